@@ -1,0 +1,263 @@
+"""ctypes binding of libdove_b200.so (the C ABI declared in include/dove_b200.h).
+
+PyTorch is used only for device memory and streams: every wrapper takes torch CUDA tensors, passes their raw
+pointers and the current CUDA stream to the C entry point and raises `DoveError` on a non-zero return code.
+There is no CPU fallback: loading fails loudly if the shared library is missing, and `init()` fails if there is
+no sm_100 device.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
+from pathlib import Path
+
+import torch
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libdove_b200.so"
+
+EPI_BIAS, EPI_GELU_TANH, EPI_GATED_RES, EPI_ADD = 0, 1, 2, 3
+
+
+class DoveError(RuntimeError):
+    pass
+
+
+_SIGS = {
+    "dove_abi_version": (c_int, []),
+    "dove_init": (c_int, [c_int]),
+    "dove_last_error": (c_char_p, []),
+    "dove_num_sms": (c_int, []),
+    "dove_gemm_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int,
+                               c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p]),
+    "dove_gemv_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "dove_layernorm_mod_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p,
+                                        c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "dove_qk_norm_rope_bf16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
+                                       c_void_p, c_void_p, c_int, c_void_p]),
+    "dove_attention_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
+    "dove_attention_bf16_variant": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_void_p]),
+    "dove_patchify_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "dove_unpatchify_velocity_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                              c_float, c_float, c_void_p]),
+    "dove_velocity_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_void_p]),
+    "dove_conv_cl_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                  c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                  c_int64, c_int, c_void_p]),
+    "dove_gn_partial_floats": (c_size_t, [c_int64, c_int]),
+    "dove_gn_stats_bf16": (c_int, [c_void_p, c_int64, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
+    "dove_gn_apply_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                   c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "dove_causal_pad_frames": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
+    "dove_time_pool_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p]),
+    "dove_upsample_nearest_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "dove_pixels_to_cl_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "dove_ncthw_to_cl_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "dove_cl_to_ncthw_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "dove_gaussian_sample_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_void_p]),
+    "dove_post_scale_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGS)
+
+_lib = None
+_inited_device = None
+
+
+def load() -> ctypes.CDLL:
+    """dlopen the in-tree library (no GPU needed); raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise DoveError(f"{LIB_PATH} is missing: run `python -m dove_b200.build` "
+                            "(dove_b200 has no CPU / PyTorch fallback path)")
+        lib = ctypes.CDLL(os.fspath(LIB_PATH))
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def init(device: int | None = None) -> None:
+    """Bind the library to a CUDA device (idempotent)."""
+    global _inited_device
+    lib = load()
+    if not torch.cuda.is_available():
+        raise DoveError("no CUDA device: dove_b200 runs only on sm_100a GPUs (no CPU fallback)")
+    if device is None:
+        device = torch.cuda.current_device()
+    if _inited_device == device:
+        return
+    rc = lib.dove_init(int(device))
+    if rc != 0:
+        raise DoveError(f"dove_init({device}) failed ({rc}): {lib.dove_last_error().decode()}")
+    _inited_device = device
+
+
+def _p(t):
+    if t is None:
+        return None
+    assert t.is_cuda, "dove_b200 kernels take CUDA tensors only"
+    return c_void_p(t.data_ptr())
+
+
+def _stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+launch_count = 0   # number of C-ABI compute calls issued (bench.py reports kernel launches from this)
+
+
+def _call(name, *args):
+    global launch_count
+    lib = load()
+    if _inited_device is None:
+        init()
+    rc = getattr(lib, name)(*args)
+    launch_count += 1
+    if rc != 0:
+        raise DoveError(f"{name} failed ({rc}): {lib.dove_last_error().decode()}")
+
+
+def _bf16c(t):
+    assert t.dtype == torch.bfloat16 and t.is_contiguous(), (t.dtype, t.is_contiguous())
+    return t
+
+
+# ---------------------------------------------------------------------------------------------- DiT ops
+def gemm(a, w, out, bias=None, epilogue=EPI_BIAS, aux=None, gate0=None, gate1=None, split_row=0):
+    """out[M,N] = epi(a[M,K] @ w[N,K]^T + bias).  a/out may be row-strided views (stride(1) == 1)."""
+    assert a.dtype == w.dtype == out.dtype == torch.bfloat16 and a.stride(1) == 1 and out.stride(1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and w.stride(1) == 1 and tuple(out.shape) == (M, N)
+    _call("dove_gemm_bf16", _p(a), a.stride(0), _p(w), w.stride(0), _p(out), out.stride(0), M, N, K, _p(bias),
+          epilogue, _p(aux), aux.stride(0) if aux is not None else 0, _p(gate0), _p(gate1), split_row, _stream())
+    return out
+
+
+def gemv(x, w, b, out, silu_in=False):
+    _call("dove_gemv_bf16", _p(_bf16c(x)), _p(_bf16c(w)), _p(b), _p(out), w.shape[0], w.shape[1], int(silu_in),
+          _stream())
+    return out
+
+
+def layernorm_mod(x, out, ln_w, ln_b, eps, scale0=None, shift0=None, scale1=None, shift1=None, split_row=0):
+    rows, D = x.shape
+    _call("dove_layernorm_mod_bf16", _p(_bf16c(x)), _p(_bf16c(out)), rows, D, _p(ln_w), _p(ln_b), eps, _p(scale0),
+          _p(shift0), _p(scale1), _p(shift1), split_row, _stream())
+    return out
+
+
+def qk_norm_rope(qkv, heads, q_w, q_b, k_w, k_b, eps, cos, sin, text_len):
+    rows = qkv.shape[0]
+    assert qkv.shape[1] == 3 * heads * 64
+    if cos is not None:
+        assert cos.dtype == torch.float32 and cos.is_contiguous() and cos.shape == (rows - text_len, 64)
+    _call("dove_qk_norm_rope_bf16", _p(_bf16c(qkv)), rows, heads, _p(q_w), _p(q_b), _p(k_w), _p(k_b), eps, _p(cos),
+          _p(sin), text_len, _stream())
+    return qkv
+
+
+def attention(qkv, out, heads, scale, variant=None):
+    rows = qkv.shape[0]
+    assert qkv.shape[1] == 3 * heads * 64 and tuple(out.shape) == (rows, heads * 64)
+    if variant is None:
+        _call("dove_attention_bf16", _p(_bf16c(qkv)), _p(_bf16c(out)), rows, heads, scale, _stream())
+    else:
+        _call("dove_attention_bf16_variant", _p(_bf16c(qkv)), _p(_bf16c(out)), rows, heads, scale, variant, _stream())
+    return out
+
+
+def patchify(latent, tokens):
+    F, C, h, w = latent.shape
+    _call("dove_patchify_bf16", _p(_bf16c(latent)), _p(_bf16c(tokens)), F, C, h, w, _stream())
+    return tokens
+
+
+def unpatchify_velocity(tokens, latent, x0, pred, F, C, h, w, a, b):
+    _call("dove_unpatchify_velocity_bf16", _p(_bf16c(tokens)), _p(latent), _p(x0), _p(pred), F, C, h, w, a, b,
+          _stream())
+
+
+def velocity(sample, noise, out, a, b):
+    _call("dove_velocity_bf16", _p(_bf16c(sample)), _p(_bf16c(noise)), _p(_bf16c(out)), sample.numel(), a, b,
+          _stream())
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- VAE ops
+def conv_cl(x, w, bias, y, Tout, kt, kh, kw, stride, pad, Ho, Wo, cout_valid, epilogue=EPI_BIAS, aux=None,
+            out_mode=0, plane_stride=0):
+    """x [Tin,Hin,Win,Cin] channels-last; w [Cout_pad, kt*kh*kw*Cin]; y [Tout,Ho,Wo,ldy] (or planar)."""
+    Tin, Hin, Win, Cin = x.shape
+    assert Tin == Tout + kt - 1, (Tin, Tout, kt)
+    Cout_pad = w.shape[0]
+    ldy = y.shape[-1] if out_mode == 0 else (plane_stride or Tout * Ho * Wo)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and y.dtype == torch.bfloat16
+    _call("dove_conv_cl_bf16", _p(x), _p(_bf16c(w)), _p(bias), _p(y), Tout, Hin, Win, Cin, Cout_pad,
+          cout_valid, ldy, kt, kh, kw, stride, pad, Ho, Wo, epilogue, _p(aux),
+          aux.shape[-1] if aux is not None else 0, out_mode, _stream())
+    return y
+
+
+def gn_partial_floats(nvox, groups=32):
+    return int(load().dove_gn_partial_floats(nvox, groups))
+
+
+def gn_stats(x, C, groups, eps, partial, stats):
+    nvox = x.numel() // C
+    _call("dove_gn_stats_bf16", _p(_bf16c(x)), nvox, C, groups, eps, _p(partial), _p(stats), _stream())
+    return stats
+
+
+def gn_apply(x, out, T, H, W, C, groups, stats, gamma, beta, silu, zq_y=None, zq_b=None):
+    Tz = hz = wz = 0
+    if zq_y is not None:
+        Tz, hz, wz, _ = zq_y.shape
+    _call("dove_gn_apply_bf16", _p(x), _p(out), T, H, W, C, groups, _p(stats), _p(gamma), _p(beta), int(silu),
+          _p(zq_y), _p(zq_b), Tz, hz, wz, _stream())
+    return out
+
+
+def causal_pad_frames(xin, T, frame_elems, cache, new_cache):
+    _call("dove_causal_pad_frames", _p(xin), T, frame_elems, _p(cache), _p(new_cache), _stream())
+
+
+def time_pool(x, y, T, frame_elems):
+    _call("dove_time_pool_bf16", _p(x), _p(y), T, frame_elems, _stream())
+    return y
+
+
+def upsample_nearest(x, y, T, H, W, C, time_x2):
+    _call("dove_upsample_nearest_bf16", _p(x), _p(y), T, H, W, C, int(time_x2), _stream())
+    return y
+
+
+def pixels_to_cl(x, y, T, H, W, Cpad):
+    assert x.dtype in (torch.float32, torch.bfloat16) and x.is_contiguous()
+    _call("dove_pixels_to_cl_bf16", _p(x), int(x.dtype == torch.float32), _p(y), T, H, W, Cpad, _stream())
+    return y
+
+
+def ncthw_to_cl(x, y, C, T, H, W, Cpad, scale=1.0):
+    _call("dove_ncthw_to_cl_bf16", _p(_bf16c(x)), _p(y), C, T, H, W, Cpad, scale, _stream())
+    return y
+
+
+def cl_to_ncthw(x, y, C, T, H, W, ldx):
+    _call("dove_cl_to_ncthw_bf16", _p(x), _p(y), C, T, H, W, ldx, _stream())
+    return y
+
+
+def gaussian_sample(moments, noise, z, nvox, scaling):
+    _call("dove_gaussian_sample_bf16", _p(moments), _p(_bf16c(noise)), _p(z), nvox, scaling, _stream())
+    return z
+
+
+def post_scale(x, y):
+    _call("dove_post_scale_bf16", _p(_bf16c(x)), _p(y), x.numel(), _stream())
+    return y

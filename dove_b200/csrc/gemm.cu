@@ -1,0 +1,425 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a, shared by
+//   * dense GEMM  C[M,N] = epi(A[M,K] W[N,K]^T + bias)           (DiT linears, VAE 1x1x1 convs)
+//   * implicit-GEMM convolution on channels-last activations      (CausalConv3d / Conv2d of the VAE)
+// The two differ only in the TMA producer: dense loads a [128 x 64] box of A; conv loads, for each filter
+// tap, the shifted [th x tw x 64ch] window of the activation tensor (4-D tensor map, OOB zero fill = spatial
+// zero padding) — no im2col buffer ever exists.
+//
+// CTA = 192 threads: warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
+// warps 2..5 = epilogue (TMEM -> registers -> fused epilogue -> global).  Accumulators are double-buffered in
+// TMEM (2 x BN fp32 columns) so the epilogue of tile i overlaps the main loop of tile i+1.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace dove {
+
+struct GemmParams {
+  int num_m_tiles, num_n_tiles, num_kb;
+  int M;   // dense: valid rows
+  // conv geometry
+  int tw, th, tiles_w, tiles_h;
+  int Ho, Wo;
+  int kh, kw, cin_blocks;
+  int stride, pad;
+  // epilogue
+  int epi;
+  bf16* C;
+  long long ldc;
+  const bf16* bias;
+  const bf16* aux;
+  long long ld_aux;
+  const bf16* gate0;
+  const bf16* gate1;
+  int split_row;
+  int n_valid;    // columns stored
+  int out_mode;   // 0 row-major [rows, ldc], 1 planar [n][rows_total]
+  long long rows_total;
+};
+
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+  // 0.5*x*(1+tanh(sqrt(2/pi)*(x+0.044715x^3))), tanh(y) = 1 - 2/(exp(2y)+1)
+  const float kBeta = 0.7978845608028654f, kKappa = 0.044715f;
+  float inner = kBeta * (x + kKappa * x * x * x);
+  float t = 1.0f - 2.0f / (__expf(2.0f * inner) + 1.0f);
+  return 0.5f * x * (1.0f + t);
+}
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr uint32_t A_BYTES = 128 * 128;
+  static constexpr uint32_t B_BYTES = BN * 128;
+  static constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
+                                        : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int CH = (BN >= 32) ? 32 : 16;
+  static constexpr size_t SMEM = 1024 + STAGES * (A_BYTES + B_BYTES) + 256;
+};
+
+template <int BN, bool kConv>
+__global__ void __launch_bounds__(192, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int CH = Cfg::CH;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::B_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int mt = tile / p.num_n_tiles, nt = tile % p.num_n_tiles;
+      int t = 0, h0 = 0, w0 = 0;
+      if (kConv) {
+        const int tpf = p.tiles_h * p.tiles_w;
+        t = mt / tpf;
+        const int r = mt - t * tpf;
+        h0 = (r / p.tiles_w) * p.th;
+        w0 = (r % p.tiles_w) * p.tw;
+      }
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_expect_tx(&full[stage], Cfg::A_BYTES + Cfg::B_BYTES);
+        if (kConv) {
+          const int tap = kb / p.cin_blocks;
+          const int c0 = (kb - tap * p.cin_blocks) * 64;
+          const int dw = tap % p.kw;
+          const int dh = (tap / p.kw) % p.kh;
+          const int dt = tap / (p.kw * p.kh);
+          tma_load_4d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], c0, w0 * p.stride + dw - p.pad,
+                      h0 * p.stride + dh - p.pad, t + dt);
+        } else {
+          tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], kb * 64, mt * 128);
+        }
+        tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * 64, nt * BN);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer (one thread) =====================
+    constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint64_t adesc = umma_desc_sw128(smem_u32(sA + stage * Cfg::A_BYTES));
+        const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + stage * Cfg::B_BYTES));
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // 4 x (K = 16) per 64-wide k-block; +32 B per step inside the swizzle atom
+          umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+        umma_commit(&empty[stage]);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(&tfull[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else if (warp >= 2) {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;               // TMEM lane quarter this warp may access
+    const int r_in_tile = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int mt = tile / p.num_n_tiles, nt = tile % p.num_n_tiles;
+      long long row;
+      bool valid;
+      if (kConv) {
+        const int tpf = p.tiles_h * p.tiles_w;
+        const int t = mt / tpf;
+        const int r = mt - t * tpf;
+        const int h = (r / p.tiles_w) * p.th + r_in_tile / p.tw;
+        const int w = (r % p.tiles_w) * p.tw + r_in_tile % p.tw;
+        valid = (h < p.Ho) && (w < p.Wo);
+        row = (static_cast<long long>(t) * p.Ho + h) * p.Wo + w;
+      } else {
+        row = static_cast<long long>(mt) * 128 + r_in_tile;
+        valid = row < p.M;
+      }
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      const bf16* gate = (p.epi == DOVE_EPI_GATED_RES) ? (row < p.split_row ? p.gate0 : p.gate1) : nullptr;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += CH) {
+        uint32_t v[CH];
+        if (CH == 32) tmem_ld32(t_row + c0, v); else tmem_ld16(t_row + c0, v);
+        tmem_ld_wait();
+        const int n0 = nt * BN + c0;
+        if (valid) {
+          float r[CH];
+#pragma unroll
+          for (int i = 0; i < CH; ++i) {
+            float x = __uint_as_float(v[i]);
+            if (p.bias) x += __bfloat162float(p.bias[n0 + i]);
+            r[i] = bf16_round(x);
+          }
+          if (p.epi == DOVE_EPI_GELU_TANH) {
+#pragma unroll
+            for (int i = 0; i < CH; ++i) r[i] = gelu_tanh_f(r[i]);
+          } else if (p.epi == DOVE_EPI_GATED_RES || p.epi == DOVE_EPI_ADD) {
+            const uint4* ap = reinterpret_cast<const uint4*>(p.aux + row * p.ld_aux + n0);
+#pragma unroll
+            for (int j = 0; j < CH / 8; ++j) {
+              const uint4 a4 = ap[j];
+              const uint32_t au[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float2 a2 = unpack_bf16x2(au[k]);
+                const int i = j * 8 + k * 2;
+                if (p.epi == DOVE_EPI_GATED_RES) {
+                  const float g0 = __bfloat162float(gate[n0 + i]), g1 = __bfloat162float(gate[n0 + i + 1]);
+                  r[i] = a2.x + bf16_round(g0 * r[i]);
+                  r[i + 1] = a2.y + bf16_round(g1 * r[i + 1]);
+                } else {
+                  r[i] += a2.x;
+                  r[i + 1] += a2.y;
+                }
+              }
+            }
+          }
+          if (p.out_mode == 0 && n0 + CH <= p.n_valid) {
+            uint4* cp = reinterpret_cast<uint4*>(p.C + row * p.ldc + n0);
+#pragma unroll
+            for (int j = 0; j < CH / 8; ++j) {
+              uint4 o;
+              o.x = pack_bf16x2(r[j * 8 + 0], r[j * 8 + 1]);
+              o.y = pack_bf16x2(r[j * 8 + 2], r[j * 8 + 3]);
+              o.z = pack_bf16x2(r[j * 8 + 4], r[j * 8 + 5]);
+              o.w = pack_bf16x2(r[j * 8 + 6], r[j * 8 + 7]);
+              cp[j] = o;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+              const int n = n0 + i;
+              if (n < p.n_valid) {
+                if (p.out_mode == 0) p.C[row * p.ldc + n] = __float2bfloat16_rn(r[i]);
+                else p.C[static_cast<long long>(n) * p.rows_total + row] = __float2bfloat16_rn(r[i]);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int BN, bool kConv>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;   // idempotent; benign race
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(umma_gemm_kernel<BN, kConv>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(Cfg::SMEM));
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(umma_gemm_kernel)");
+    attr_set = true;
+  }
+  const int total = p.num_m_tiles * p.num_n_tiles;
+  const int grid = total < num_sms() ? total : num_sms();
+  umma_gemm_kernel<BN, kConv><<<grid, 192, Cfg::SMEM, st>>>(tmA, tmB, p);
+  DOVE_LAUNCH_CHECK("umma_gemm_kernel");
+  return DOVE_OK;
+}
+
+template <bool kConv>
+static int dispatch_bn(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
+                       cudaStream_t st) {
+  switch (bn) {
+    case 256: return launch_gemm<256, kConv>(tmA, tmB, p, st);
+    case 128: return launch_gemm<128, kConv>(tmA, tmB, p, st);
+    case 64: return launch_gemm<64, kConv>(tmA, tmB, p, st);
+    case 32: return launch_gemm<32, kConv>(tmA, tmB, p, st);
+    case 16: return launch_gemm<16, kConv>(tmA, tmB, p, st);
+  }
+  return set_error(DOVE_E_BAD_ARG, "unsupported BN %d", bn);
+}
+
+static int pick_bn(int N) {
+  if (N % 256 == 0) return 256;
+  if (N % 128 == 0) return 128;
+  if (N % 64 == 0) return 64;
+  if (N % 32 == 0) return 32;
+  return 16;
+}
+
+}  // namespace dove
+
+using namespace dove;
+
+extern "C" int dove_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M,
+                              int N, int K, const void* bias, int epilogue, const void* aux, int64_t ld_aux,
+                              const void* gate0, const void* gate1, int split_row, void* stream) {
+  if (int e = ensure_init()) return e;
+  DOVE_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  DOVE_CHECK_ARG(K % 64 == 0, "gemm: K=%d must be a multiple of 64", K);
+  DOVE_CHECK_ARG(N % 16 == 0, "gemm: N=%d must be a multiple of 16", N);
+  DOVE_CHECK_ARG(lda % 8 == 0 && ldw % 8 == 0 && ldc % 8 == 0, "gemm: leading dims must be multiples of 8");
+  DOVE_CHECK_ARG((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) |
+                  reinterpret_cast<uintptr_t>(C)) % 16 == 0, "gemm: pointers must be 16-byte aligned");
+  DOVE_CHECK_ARG(epilogue >= 0 && epilogue <= 3, "gemm: bad epilogue %d", epilogue);
+  if (epilogue == DOVE_EPI_GATED_RES)
+    DOVE_CHECK_ARG(aux && gate0 && gate1 && ld_aux % 8 == 0, "gemm: gated residual needs aux, gate0, gate1");
+  if (epilogue == DOVE_EPI_ADD) DOVE_CHECK_ARG(aux && ld_aux % 8 == 0, "gemm: add epilogue needs aux");
+  const int bn = pick_bn(N);
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
+    uint64_t strides[1] = {static_cast<uint64_t>(lda) * 2};
+    uint32_t box[2] = {64, 128};
+    if (int e = make_tmap_bf16(&tmA, A, 2, dims, strides, box, nullptr)) return e;
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+    uint64_t strides[1] = {static_cast<uint64_t>(ldw) * 2};
+    uint32_t box[2] = {64, static_cast<uint32_t>(bn)};
+    if (int e = make_tmap_bf16(&tmB, W, 2, dims, strides, box, nullptr)) return e;
+  }
+  GemmParams p{};
+  p.num_m_tiles = (M + 127) / 128;
+  p.num_n_tiles = N / bn;
+  p.num_kb = K / 64;
+  p.M = M;
+  p.epi = epilogue;
+  p.C = static_cast<bf16*>(C);
+  p.ldc = ldc;
+  p.bias = static_cast<const bf16*>(bias);
+  p.aux = static_cast<const bf16*>(aux);
+  p.ld_aux = ld_aux;
+  p.gate0 = static_cast<const bf16*>(gate0);
+  p.gate1 = static_cast<const bf16*>(gate1);
+  p.split_row = split_row;
+  p.n_valid = N;
+  p.out_mode = 0;
+  p.rows_total = M;
+  return dispatch_bn<false>(bn, tmA, tmB, p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int dove_conv_cl_bf16(const void* x, const void* w, const void* bias, void* y, int Tout, int Hin,
+                                 int Win, int Cin, int Cout_pad, int cout_valid, int64_t ldy, int kt, int kh,
+                                 int kw, int stride, int pad, int Ho, int Wo, int epilogue, const void* aux,
+                                 int64_t ld_aux, int out_mode, void* stream) {
+  if (int e = ensure_init()) return e;
+  DOVE_CHECK_ARG(Tout > 0 && Hin > 0 && Win > 0 && Ho > 0 && Wo > 0, "conv: empty problem");
+  DOVE_CHECK_ARG(Cin % 64 == 0, "conv: Cin=%d must be a multiple of 64 (pad channels)", Cin);
+  DOVE_CHECK_ARG(Cout_pad % 16 == 0 && cout_valid <= Cout_pad, "conv: Cout_pad=%d must be a multiple of 16", Cout_pad);
+  DOVE_CHECK_ARG(stride == 1 || stride == 2, "conv: stride must be 1 or 2");
+  DOVE_CHECK_ARG(epilogue == DOVE_EPI_BIAS || epilogue == DOVE_EPI_ADD, "conv: epilogue must be BIAS or ADD");
+  DOVE_CHECK_ARG(out_mode == 0 || out_mode == 1, "conv: bad out_mode");
+  if (out_mode == 0) DOVE_CHECK_ARG(ldy % 8 == 0, "conv: ldy must be a multiple of 8");
+  if (out_mode == 1) DOVE_CHECK_ARG(ldy >= static_cast<long long>(Tout) * Ho * Wo, "conv: planar plane stride too small");
+  if (epilogue == DOVE_EPI_ADD) DOVE_CHECK_ARG(aux && ld_aux % 8 == 0, "conv: add epilogue needs aux");
+  const int bn = pick_bn(Cout_pad);
+  // output tile geometry: tw x th = 128 voxels of one frame, tw a power of two minimising padded waste
+  int best_tw = 128;
+  long long best_cost = -1;
+  for (int tw = 128; tw >= 8; tw >>= 1) {
+    const int th = 128 / tw;
+    if (stride == 2 && (tw * 2 > 256 || th * 2 > 256)) continue;
+    const long long cost = static_cast<long long>((Wo + tw - 1) / tw) * ((Ho + th - 1) / th);
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best_tw = tw;
+    }
+  }
+  const int tw = best_tw, th = 128 / tw;
+  const int Tin = Tout + kt - 1;
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[4] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(Win), static_cast<uint64_t>(Hin),
+                        static_cast<uint64_t>(Tin)};
+    uint64_t strides[3] = {static_cast<uint64_t>(Cin) * 2, static_cast<uint64_t>(Win) * Cin * 2,
+                           static_cast<uint64_t>(Hin) * Win * Cin * 2};
+    uint32_t box[4] = {64, static_cast<uint32_t>(tw * stride), static_cast<uint32_t>(th * stride), 1};
+    uint32_t es[4] = {1, static_cast<uint32_t>(stride), static_cast<uint32_t>(stride), 1};
+    if (int e = make_tmap_bf16(&tmA, x, 4, dims, strides, box, es)) return e;
+  }
+  const int Ktot = kt * kh * kw * Cin;
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(Ktot), static_cast<uint64_t>(Cout_pad)};
+    uint64_t strides[1] = {static_cast<uint64_t>(Ktot) * 2};
+    uint32_t box[2] = {64, static_cast<uint32_t>(bn)};
+    if (int e = make_tmap_bf16(&tmB, w, 2, dims, strides, box, nullptr)) return e;
+  }
+  GemmParams p{};
+  p.tw = tw;
+  p.th = th;
+  p.tiles_w = (Wo + tw - 1) / tw;
+  p.tiles_h = (Ho + th - 1) / th;
+  p.num_m_tiles = Tout * p.tiles_w * p.tiles_h;
+  p.num_n_tiles = Cout_pad / bn;
+  p.num_kb = Ktot / 64;
+  p.Ho = Ho;
+  p.Wo = Wo;
+  p.kh = kh;
+  p.kw = kw;
+  p.cin_blocks = Cin / 64;
+  p.stride = stride;
+  p.pad = pad;
+  p.epi = epilogue;
+  p.C = static_cast<bf16*>(y);
+  p.ldc = ldy;
+  p.bias = static_cast<const bf16*>(bias);
+  p.aux = static_cast<const bf16*>(aux);
+  p.ld_aux = ld_aux;
+  p.n_valid = cout_valid;
+  p.out_mode = out_mode;
+  p.rows_total = out_mode == 1 ? ldy : static_cast<long long>(Tout) * Ho * Wo;
+  return dispatch_bn<true>(bn, tmA, tmB, p, static_cast<cudaStream_t>(stream));
+}

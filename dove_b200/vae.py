@@ -1,0 +1,337 @@
+"""B200-native CogVideoX 3-D causal VAE (host orchestration over libdove_b200 kernels).
+
+Mirror of the diffusers `AutoencoderKLCogVideoX` surface used by the reference:
+  pipe.vae.encode(x).latent_dist.sample()   ref: /root/reference/inference_script.py:408-409
+  pipe.vae.decode(z).sample (via pipe.decode_latents)               :500
+  pipe.vae.config.scaling_factor / block_out_channels                :409, :467
+  pipe.vae.enable_slicing() / enable_tiling()                        :643-645
+  pipe.vae.device / dtype                                            :407
+
+Data layout in HBM: every activation is CHANNELS-LAST bf16 [T, H, W, C] (C contiguous) so a convolution tap is
+a plain 4-D TMA box [th, tw, 64ch] of the input; causal 3x3x3 convs read from a temporally padded buffer
+[T+2, H, W, C] whose 2 leading frames are the conv cache (CogVideoXCausalConv3d semantics).  Frame batching
+(8 pixel frames / 2 latent frames, first batch takes the remainder) and the per-conv cache follow
+`AutoencoderKLCogVideoX._encode/_decode`.
+
+Kernel sequence per ResnetBlock3D:  gn_stats -> gn_apply(+SiLU, writes straight into the padded conv input)
+-> causal_pad_frames -> conv (tcgen05 implicit GEMM) -> gn_stats -> gn_apply -> causal_pad_frames ->
+[1x1x1 shortcut GEMM] -> conv with the residual add fused in the epilogue.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+
+import torch
+
+from . import _lib as L
+from .weights import VAE_CONFIG
+
+BF = torch.bfloat16
+
+
+def _pad_to(n, m):
+    return (n + m - 1) // m * m
+
+
+class _Conv:
+    """Weights of one conv in implicit-GEMM layout [Cout_pad, kt*kh*kw*Cin_pad], K index = tap*Cin_pad + c."""
+
+    def __init__(self, w, b, device):
+        if w.dim() == 4:      # Conv2d [Cout, Cin, kh, kw]
+            w = w[:, :, None]
+        cout, cin, kt, kh, kw = w.shape
+        self.cin, self.cout, self.kt, self.kh, self.kw = cin, cout, kt, kh, kw
+        self.cin_pad = _pad_to(cin, 64)
+        self.cout_pad = _pad_to(cout, 16)
+        wp = torch.zeros(self.cout_pad, kt, kh, kw, self.cin_pad, dtype=BF, device=device)
+        wp[:cout, :, :, :, :cin] = w.to(device=device, dtype=BF).permute(0, 2, 3, 4, 1)
+        self.w = wp.reshape(self.cout_pad, kt * kh * kw * self.cin_pad).contiguous()
+        bp = torch.zeros(self.cout_pad, dtype=BF, device=device)
+        bp[:cout] = b.to(device=device, dtype=BF)
+        self.b = bp
+
+
+class _Norm:
+    def __init__(self, sd, name, device, spatial):
+        pre = f"{name}.norm_layer" if spatial else name
+        self.gamma = sd[f"{pre}.weight"].to(device=device, dtype=BF).contiguous()
+        self.beta = sd[f"{pre}.bias"].to(device=device, dtype=BF).contiguous()
+        self.spatial = spatial
+        if spatial:
+            self.conv_y = _Conv(sd[f"{name}.conv_y.conv.weight"], sd[f"{name}.conv_y.conv.bias"], device)
+            self.conv_b = _Conv(sd[f"{name}.conv_b.conv.weight"], sd[f"{name}.conv_b.conv.bias"], device)
+
+
+class _Resnet:
+    def __init__(self, sd, name, device, spatial):
+        self.name = name
+        self.norm1 = _Norm(sd, f"{name}.norm1", device, spatial)
+        self.norm2 = _Norm(sd, f"{name}.norm2", device, spatial)
+        self.conv1 = _Conv(sd[f"{name}.conv1.conv.weight"], sd[f"{name}.conv1.conv.bias"], device)
+        self.conv2 = _Conv(sd[f"{name}.conv2.conv.weight"], sd[f"{name}.conv2.conv.bias"], device)
+        self.shortcut = None
+        if f"{name}.conv_shortcut.weight" in sd:
+            self.shortcut = _Conv(sd[f"{name}.conv_shortcut.weight"], sd[f"{name}.conv_shortcut.bias"], device)
+
+
+class LatentDistribution:
+    """DiagonalGaussianDistribution over channels-last moments [T, h, w, 32] (mean | logvar)."""
+
+    def __init__(self, moments_cl, shape):
+        self._m = moments_cl
+        self._shape = shape      # (T, h, w)
+
+    @property
+    def parameters(self):
+        T, h, w = self._shape
+        out = torch.empty(1, 32, T, h, w, dtype=BF, device=self._m.device)
+        L.cl_to_ncthw(self._m, out, 32, T, h, w, 32)
+        return out
+
+    def sample(self, generator=None, noise=None, scaling=1.0):
+        """mean + std * randn.  Exactly one `torch.randn` of shape [1,16,T,h,w] is drawn from the global CUDA
+        generator (same stream semantics as diffusers' randn_tensor)."""
+        T, h, w = self._shape
+        if noise is None:
+            noise = torch.randn((1, 16, T, h, w), generator=generator, device=self._m.device, dtype=BF)
+        z = torch.empty(1, 16, T, h, w, dtype=BF, device=self._m.device)
+        L.gaussian_sample(self._m, noise.contiguous(), z, T * h * w, scaling)
+        return z
+
+    def mode(self):
+        return self.parameters[:, :16].contiguous()
+
+
+class AutoencoderKLCogVideoX:
+    def __init__(self, state_dict, config=None, device="cuda"):
+        cfg = dict(VAE_CONFIG)
+        cfg.update(config or {})
+        self.config = SimpleNamespace(**cfg)
+        self._device = torch.device(device)
+        if self._device.type != "cuda":
+            raise L.DoveError("dove_b200.AutoencoderKLCogVideoX runs on CUDA (sm_100a) only")
+        L.init(self._device.index if self._device.index is not None else torch.cuda.current_device())
+        self.use_tiling = False
+        self.use_slicing = False
+        self.num_latent_frames_batch_size = 2
+        self.num_sample_frames_batch_size = 8
+        self._build(state_dict)
+        self._partial = torch.empty(L.gn_partial_floats(0), dtype=torch.float32, device=self._device)
+
+    # ---- surface ----------------------------------------------------------------------------------
+    @property
+    def device(self):
+        return self._device
+
+    @property
+    def dtype(self):
+        return BF
+
+    def to(self, *a, **k):
+        return self
+
+    def enable_slicing(self):
+        self.use_slicing = True      # no-op at batch 1 (diffusers slices over the batch dim)
+
+    def enable_tiling(self):
+        self.use_tiling = True
+
+    # ---- weights ----------------------------------------------------------------------------------
+    def _build(self, sd):
+        dev = self._device
+        c = self.config
+        boc = list(c.block_out_channels)
+        lpb = c.layers_per_block
+        conv = lambda n: _Conv(sd[f"{n}.weight"], sd[f"{n}.bias"], dev)
+        self.enc_conv_in = conv("encoder.conv_in.conv")
+        self.enc_down = []
+        for i in range(len(boc)):
+            res = [_Resnet(sd, f"encoder.down_blocks.{i}.resnets.{j}", dev, False) for j in range(lpb)]
+            down = conv(f"encoder.down_blocks.{i}.downsamplers.0.conv") if i != len(boc) - 1 else None
+            self.enc_down.append((res, down, i < 2))
+        self.enc_mid = [_Resnet(sd, f"encoder.mid_block.resnets.{j}", dev, False) for j in range(2)]
+        self.enc_norm_out = _Norm(sd, "encoder.norm_out", dev, False)
+        self.enc_conv_out = conv("encoder.conv_out.conv")
+        self.dec_conv_in = conv("decoder.conv_in.conv")
+        self.dec_mid = [_Resnet(sd, f"decoder.mid_block.resnets.{j}", dev, True) for j in range(2)]
+        self.dec_up = []
+        for i in range(len(boc)):
+            res = [_Resnet(sd, f"decoder.up_blocks.{i}.resnets.{j}", dev, True) for j in range(lpb + 1)]
+            up = conv(f"decoder.up_blocks.{i}.upsamplers.0.conv") if i != len(boc) - 1 else None
+            self.dec_up.append((res, up, i < 2))
+        self.dec_norm_out = _Norm(sd, "decoder.norm_out", dev, True)
+        self.dec_conv_out = conv("decoder.conv_out.conv")
+
+    # ---- building blocks (channels-last) ---------------------------------------------------------------
+    def _empty(self, *shape):
+        return torch.empty(*shape, dtype=BF, device=self._device)
+
+    def _norm_into_padded(self, norm, x, T, H, W, C, zq, silu=True):
+        """GroupNorm / SpatialNorm3D (+SiLU) of x [T,H,W,C] written into a fresh padded buffer [T+2,H,W,C]."""
+        stats = torch.empty(64, dtype=torch.float32, device=self._device)
+        L.gn_stats(x, C, 32, self.config.norm_eps, self._partial, stats)
+        xin = self._empty(T + 2, H, W, C)
+        zy = zb = None
+        if norm.spatial:
+            zq_cl, (Tz, hz, wz) = zq
+            nvz = Tz * hz * wz
+            zy = self._empty(Tz, hz, wz, C)
+            zb = self._empty(Tz, hz, wz, C)
+            L.gemm(zq_cl.view(nvz, 64), norm.conv_y.w, zy.view(nvz, C), norm.conv_y.b)
+            L.gemm(zq_cl.view(nvz, 64), norm.conv_b.w, zb.view(nvz, C), norm.conv_b.b)
+        L.gn_apply(x, xin[2:], T, H, W, C, 32, stats, norm.gamma, norm.beta, silu, zy, zb)
+        return xin
+
+    def _causal_conv(self, conv, xin, T, H, W, cache, key, out=None, aux=None, out_mode=0, plane_stride=0):
+        """xin: padded [T+2,H,W,Cin_pad] with frames 2.. already written.  Fills the 2 leading frames from the
+        cache (or by replicating frame 0), saves the new cache, runs the conv."""
+        fe = H * W * conv.cin_pad
+        old = cache.get(key)
+        new = old if old is not None else self._empty(2, H, W, conv.cin_pad)
+        L.causal_pad_frames(xin, T, fe, old, new)
+        cache[key] = new
+        if out is None:
+            out = self._empty(T, H, W, conv.cout_pad)
+        L.conv_cl(xin, conv.w, conv.b, out, T, 3, 3, 3, 1, 1, H, W, conv.cout,
+                  epilogue=L.EPI_ADD if aux is not None else L.EPI_BIAS, aux=aux, out_mode=out_mode,
+                  plane_stride=plane_stride)
+        return out
+
+    def _resnet(self, r, x, T, H, W, zq, cache):
+        cin, cout = r.conv1.cin, r.conv1.cout
+        xin = self._norm_into_padded(r.norm1, x, T, H, W, cin, zq)
+        h = self._causal_conv(r.conv1, xin, T, H, W, cache, r.name + ".conv1")
+        del xin
+        xin2 = self._norm_into_padded(r.norm2, h, T, H, W, cout, zq)
+        del h
+        if r.shortcut is not None:
+            nv = T * H * W
+            res = self._empty(T, H, W, cout)
+            L.gemm(x.view(nv, cin), r.shortcut.w, res.view(nv, cout), r.shortcut.b)
+        else:
+            res = x
+        return self._causal_conv(r.conv2, xin2, T, H, W, cache, r.name + ".conv2", aux=res)
+
+    # ---- encoder ----------------------------------------------------------------------------------
+    def _encoder_batch(self, pix, t0, t1, F, H, W, cache):
+        """pix: [3, F, H, W] (fp32 or bf16) contiguous; frames t0..t1 -> moments [T', H/8, W/8, 32]."""
+        T = t1 - t0
+        xin = self._empty(T + 2, H, W, 64)
+        # per-channel planes of this frame batch are strided inside pix: gather through a contiguous view
+        src = pix[:, t0:t1].contiguous() if (t0 != 0 or t1 != F) else pix
+        L.pixels_to_cl(src, xin[2:], T, H, W, 64)
+        x = self._causal_conv(self.enc_conv_in, xin, T, H, W, cache, "conv_in")
+        del xin
+        for bi, (res, down, compress_time) in enumerate(self.enc_down):
+            for r in res:
+                x = self._resnet(r, x, T, H, W, None, cache)
+            if down is not None:
+                C = down.cin
+                if compress_time:
+                    To = 1 + (T - 1) // 2 if T % 2 else T // 2
+                    y = self._empty(To, H, W, C)
+                    L.time_pool(x, y, T, H * W * C)
+                    x, T = y, To
+                Ho, Wo = H // 2, W // 2
+                y = self._empty(T, Ho, Wo, C)
+                L.conv_cl(x, down.w, down.b, y, T, 1, 3, 3, 2, 0, Ho, Wo, down.cout)
+                x, H, W = y, Ho, Wo
+        for r in self.enc_mid:
+            x = self._resnet(r, x, T, H, W, None, cache)
+        C = self.enc_conv_out.cin
+        xin = self._norm_into_padded(self.enc_norm_out, x, T, H, W, C, None)
+        return self._causal_conv(self.enc_conv_out, xin, T, H, W, cache, "conv_out"), (T, H, W)
+
+    @staticmethod
+    def frame_batches(num_frames, bs):
+        nb = max(num_frames // bs, 1)
+        rem = num_frames % bs
+        return [(bs * i + (0 if i == 0 else rem), bs * (i + 1) + rem) for i in range(nb)]
+
+    def _check_tiling(self, h, w, min_h, min_w):
+        if self.use_tiling and (w > min_w or h > min_h):
+            raise NotImplementedError(
+                "VAE spatial tiling (--is_vae_st / enable_tiling) is the 'next' row f-2 of SURVEY.md section 8 and "
+                "is not implemented yet; 180 GB of HBM fits the untiled pass, run without enable_tiling()")
+
+    def encode_cl(self, x):
+        """x: [1,3,F,H,W] on device (fp32 or bf16) -> (moments channels-last [T',h,w,32], (T',h,w))."""
+        assert x.dim() == 5 and x.shape[0] == 1 and x.shape[1] == 3, "batch 1, 3 channels"
+        _, _, F, H, W = x.shape
+        assert H % 8 == 0 and W % 8 == 0, "H, W must be multiples of 8"
+        self._check_tiling(H, W, self.config.sample_height // 2, self.config.sample_width // 2)
+        pix = x[0].contiguous()
+        cache = {}
+        outs, shape = [], None
+        for (s, e) in self.frame_batches(F, self.num_sample_frames_batch_size):
+            m, shp = self._encoder_batch(pix, s, e, F, H, W, cache)
+            outs.append(m)
+            shape = shp
+        mom = torch.cat(outs, dim=0) if len(outs) > 1 else outs[0]
+        return mom, (mom.shape[0], shape[1], shape[2])
+
+    def encode(self, x):
+        x = x.to(self._device)
+        if x.dtype not in (torch.float32, BF):
+            x = x.to(BF)
+        mom, shape = self.encode_cl(x)
+        return SimpleNamespace(latent_dist=LatentDistribution(mom, shape))
+
+    # ---- decoder ----------------------------------------------------------------------------------
+    def _decoder_batch(self, z, t0, t1, h, w, scale, cache, out, f_off, F_out):
+        """z: [16, Tz_total, h, w] bf16; latent frames t0..t1 -> pixels written into out[3, F_out, 8h, 8w]."""
+        T = t1 - t0
+        zsrc = z[:, t0:t1].contiguous()
+        xin = self._empty(T + 2, h, w, 64)
+        L.ncthw_to_cl(zsrc, xin[2:], 16, T, h, w, 64, scale)
+        zq = (xin[2:], (T, h, w))                     # the (scaled) latent batch conditions every SpatialNorm3D
+        x = self._causal_conv(self.dec_conv_in, xin, T, h, w, cache, "conv_in")
+        H, W = h, w
+        for r in self.dec_mid:
+            x = self._resnet(r, x, T, H, W, zq, cache)
+        for (res, up, compress_time) in self.dec_up:
+            for r in res:
+                x = self._resnet(r, x, T, H, W, zq, cache)
+            if up is not None:
+                C = up.cin
+                if compress_time and T > 1:
+                    To = 1 + 2 * (T - 1) if T % 2 else 2 * T
+                else:
+                    To = T
+                y = self._empty(To, 2 * H, 2 * W, C)
+                L.upsample_nearest(x, y, T, H, W, C, compress_time)
+                x, T, H, W = y, To, 2 * H, 2 * W
+                y = self._empty(T, H, W, C)
+                L.conv_cl(x, up.w, up.b, y, T, 1, 3, 3, 1, 1, H, W, up.cout)
+                x = y
+        C = self.dec_conv_out.cin
+        xin2 = self._norm_into_padded(self.dec_norm_out, x, T, H, W, C, zq)
+        del x
+        # conv_out writes planar NCDHW straight into the output clip at frame offset f_off
+        self._causal_conv(self.dec_conv_out, xin2, T, H, W, cache, "conv_out",
+                          out=out.view(3, -1)[:, f_off * H * W:], out_mode=1, plane_stride=F_out * H * W)
+        return T
+
+    def decode_scaled(self, z, scale=1.0):
+        """z: [1,16,Tz,h,w] bf16 -> [1,3,F,8h,8w] bf16; `scale` is applied to z first (decode_latents' 1/0.7)."""
+        assert z.dim() == 5 and z.shape[0] == 1 and z.shape[1] == 16
+        _, _, Tz, h, w = z.shape
+        sf = 2 ** (len(self.config.block_out_channels) - 1)
+        self._check_tiling(h, w, self.config.sample_height // 2 // sf, self.config.sample_width // 2 // sf)
+        batches = self.frame_batches(Tz, self.num_latent_frames_batch_size)
+        F_out = 0
+        for bi, (s, e) in enumerate(batches):     # frames produced: first batch keeps frame 0 single
+            T = e - s
+            for _ in range(2):
+                T = (1 + 2 * (T - 1) if T % 2 else 2 * T) if T > 1 else T
+            F_out += T
+        out = self._empty(1, 3, F_out, h * sf, w * sf)
+        zc = z[0].to(BF).contiguous()
+        cache = {}
+        f_off = 0
+        for (s, e) in batches:
+            f_off += self._decoder_batch(zc, s, e, h, w, scale, cache, out[0], f_off, F_out)
+        return out
+
+    def decode(self, z):
+        return SimpleNamespace(sample=self.decode_scaled(z.to(self._device), 1.0))
