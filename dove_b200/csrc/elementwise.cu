@@ -208,12 +208,11 @@ constexpr int GN_MAX_BLOCKS = 1184;
 // x [nvox, C] channels-last.  thread -> fixed 8-channel vector column, strided over voxels.
 __global__ void __launch_bounds__(256) gn_partial_kernel(const bf16* __restrict__ x, long long nvox, int C,
                                                          int groups, float* __restrict__ partial) {
-  __shared__ float sh[64];
+  // per-thread partials are combined in a FIXED order (no atomics) so results are run-to-run deterministic
+  __shared__ float sh[256 * 4];
   const int vcols = C >> 3;
   const int vcol = threadIdx.x % vcols, vlane = threadIdx.x / vcols, vper = blockDim.x / vcols;
   const int cpg = C / groups;
-  if (threadIdx.x < 64) sh[threadIdx.x] = 0.f;
-  __syncthreads();
   float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
   for (long long v = static_cast<long long>(blockIdx.x) * vper + vlane; v < nvox;
        v += static_cast<long long>(gridDim.x) * vper) {
@@ -224,18 +223,24 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const bf16* __restrict_
 #pragma unroll
     for (int k = 4; k < 8; ++k) { s1 += f[k]; q1 += f[k] * f[k]; }
   }
-  if (cpg == 4) {
-    atomicAdd(&sh[(vcol * 2) * 2], s0);
-    atomicAdd(&sh[(vcol * 2) * 2 + 1], q0);
-    atomicAdd(&sh[(vcol * 2 + 1) * 2], s1);
-    atomicAdd(&sh[(vcol * 2 + 1) * 2 + 1], q1);
-  } else {
-    const int g = vcol * 8 / cpg;
-    atomicAdd(&sh[g * 2], s0 + s1);
-    atomicAdd(&sh[g * 2 + 1], q0 + q1);
-  }
+  sh[threadIdx.x * 4 + 0] = s0;
+  sh[threadIdx.x * 4 + 1] = q0;
+  sh[threadIdx.x * 4 + 2] = s1;
+  sh[threadIdx.x * 4 + 3] = q1;
   __syncthreads();
-  if (threadIdx.x < groups * 2) partial[static_cast<long long>(blockIdx.x) * groups * 2 + threadIdx.x] = sh[threadIdx.x];
+  if (threadIdx.x < groups * 2) {
+    const int g = threadIdx.x >> 1, which = threadIdx.x & 1;   // which: 0 = sum, 1 = sum of squares
+    float acc = 0.f;
+    for (int t = 0; t < 256; ++t) {
+      const int tv = t % vcols;
+      if (cpg == 4) {
+        if (tv == (g >> 1)) acc += sh[t * 4 + (g & 1) * 2 + which];
+      } else if (tv * 8 / cpg == g) {
+        acc += sh[t * 4 + which] + sh[t * 4 + 2 + which];
+      }
+    }
+    partial[static_cast<long long>(blockIdx.x) * groups * 2 + threadIdx.x] = acc;
+  }
 }
 
 __global__ void gn_finalize_kernel(const float* __restrict__ partial, int nblocks, int groups, double count,

@@ -1,0 +1,123 @@
+"""Clip-level driver: temporal-chunk x spatial-tile unit loop, stitching, and unit sharding over GPUs.
+
+Mirrors the per-video hot loop of the reference (ref: /root/reference/inference_script.py:682-729):
+units = chunks x tiles in loop order; each unit is super-resolved independently; only its "valid" interior
+(half the overlap trimmed on interior sides, no blending) is written; every output voxel must be written exactly
+once or the run aborts.  B200-first differences: the stitched output stays in HBM (one D2H at the end instead of
+one synchronous D2H per unit, ref :712-717), and with world_size > 1 the units are statically partitioned
+round-robin over ranks (no data-path collective while computing) followed by ONE all-gather of the packed valid
+regions — NCCL over NVLink on GPUs, gloo in the CPU tests of this host logic.
+
+RNG: the reference draws each unit's latent noise from the global generator in loop order (seed 42 once,
+ref :577), so unit k's noise depends on all earlier units.  `noise_mode="global"` reproduces that (single rank
+only).  `noise_mode="per_unit"` seeds unit k with `seed + k`, which makes results independent of the rank
+count; it is required (and the default) when world_size > 1.
+"""
+from __future__ import annotations
+
+import torch
+
+from .bookkeeping import enumerate_units, get_valid_tile_region, partition_units
+
+
+class StitchError(RuntimeError):
+    """write count != 1 somewhere (the reference prints and exit()s, ref :724-729)."""
+
+
+def _unit_regions(units, video_shape, overlap_t, overlap_hw):
+    regs = []
+    for (t0, t1), (h0, h1, w0, w1) in units:
+        regs.append(get_valid_tile_region(t0, t1, h0, h1, w0, w1, video_shape, overlap_t, overlap_hw[0],
+                                          overlap_hw[1]))
+    return regs
+
+
+def _region_numel(r, C):
+    return (C * (r["out_t_end"] - r["out_t_start"]) * (r["out_h_end"] - r["out_h_start"]) *
+            (r["out_w_end"] - r["out_w_start"]))
+
+
+def super_resolve(video, process_fn, *, chunk_len=0, overlap_t=8, tile_size_hw=(0, 0), overlap_hw=(32, 32),
+                  out_device=None, out_dtype=None, group=None, noise_mode=None, seed=42):
+    """video: [1,3,F,H,W] float in [-1,1] (already x4-upscaled and padded, ref :670-679).
+    process_fn(unit_video, unit_index, generator_seed_or_None) -> [1,3,t,h,w] tensor in [0,1].
+    Returns the stitched [1,3,F,H,W] clip (on every rank when sharded)."""
+    import torch.distributed as dist
+    sharded = group is not None or (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
+    rank = dist.get_rank(group) if sharded else 0
+    world = dist.get_world_size(group) if sharded else 1
+    if noise_mode is None:
+        noise_mode = "per_unit" if world > 1 else "global"
+    if world > 1 and noise_mode != "per_unit":
+        raise ValueError("sharded runs need noise_mode='per_unit' (the global RNG stream is sequential)")
+    B, C, F, H, W = video.shape
+    units = enumerate_units(video.shape, chunk_len, overlap_t, tile_size_hw, overlap_hw)
+    regions = _unit_regions(units, video.shape, overlap_t, overlap_hw)
+    mine = partition_units(units, world)[rank]
+
+    results = {}
+    for k in mine:
+        (t0, t1), (h0, h1, w0, w1) = units[k]
+        unit = video[:, :, t0:t1, h0:h1, w0:w1]
+        res = process_fn(unit, k, (seed + k) if noise_mode == "per_unit" else None)
+        r = regions[k]
+        results[k] = res[:, :, r["valid_t_start"]:r["valid_t_end"], r["valid_h_start"]:r["valid_h_end"],
+                         r["valid_w_start"]:r["valid_w_end"]]
+    any_res = next(iter(results.values())) if results else None
+    dev = out_device or (any_res.device if any_res is not None else video.device)
+    dt = out_dtype or (any_res.dtype if any_res is not None else video.dtype)
+    if world > 1:   # every rank must agree on dtype/device kind; they do by construction (same process_fn)
+        dev = out_device or (any_res.device if any_res is not None else torch.device("cpu"))
+
+    out = torch.zeros((B, C, F, H, W), dtype=dt, device=dev)
+    count = torch.zeros((F, H, W), dtype=torch.int32, device=dev)
+
+    def write(k, block):
+        r = regions[k]
+        sl = (slice(r["out_t_start"], r["out_t_end"]), slice(r["out_h_start"], r["out_h_end"]),
+              slice(r["out_w_start"], r["out_w_end"]))
+        out[(slice(None), slice(None)) + sl] = block.to(device=dev, dtype=dt)
+        count[sl] += 1
+
+    if world == 1:
+        for k, block in results.items():
+            write(k, block)
+    else:
+        parts = partition_units(units, world)
+        lens = [sum(_region_numel(regions[k], B * C) for k in p) for p in parts]
+        maxlen = max(max(lens), 1)
+        send = torch.zeros(maxlen, dtype=dt, device=dev)
+        off = 0
+        for k in mine:
+            n = _region_numel(regions[k], B * C)
+            send[off:off + n] = results[k].to(device=dev, dtype=dt).reshape(-1)
+            off += n
+        recv = torch.empty(world * maxlen, dtype=dt, device=dev)
+        dist.all_gather_into_tensor(recv, send, group=group)          # the single collective of the path
+        for r_ in range(world):
+            off = r_ * maxlen
+            for k in parts[r_]:
+                rg = regions[k]
+                shp = (B, C, rg["out_t_end"] - rg["out_t_start"], rg["out_h_end"] - rg["out_h_start"],
+                       rg["out_w_end"] - rg["out_w_start"])
+                n = _region_numel(rg, B * C)
+                write(k, recv[off:off + n].view(shp))
+                off += n
+    if not bool((count == 1).all()):
+        bad = int((count != 1).sum())
+        raise StitchError(f"write count != 1 at {bad} positions (overlaps must be even and tiles must cover the clip)")
+    return out
+
+
+def make_process_fn(pipe, empty_prompt_embedding, sr_noise_step=399, noise_step=0):
+    """process_fn for `super_resolve` backed by the fused device path of `pipe`."""
+    def fn(unit, k, unit_seed):
+        noise = None
+        if unit_seed is not None:
+            _, _, F, H, W = unit.shape
+            g = torch.Generator(device=pipe.device).manual_seed(int(unit_seed))
+            tl = pipe.vae.latent_frames(F)
+            noise = torch.randn((1, 16, tl, H // 8, W // 8), generator=g, device=pipe.device, dtype=torch.bfloat16)
+        return pipe.one_step_sr(unit, empty_prompt_embedding, sr_noise_step=sr_noise_step, noise=noise,
+                                noise_step=noise_step)
+    return fn

@@ -248,6 +248,17 @@ class AutoencoderKLCogVideoX:
         rem = num_frames % bs
         return [(bs * i + (0 if i == 0 else rem), bs * (i + 1) + rem) for i in range(nb)]
 
+    @classmethod
+    def latent_frames(cls, num_frames, bs=8, levels=2):
+        """Latent frame count of `_encode` for a clip of num_frames (frame batching + 2 temporal poolings)."""
+        total = 0
+        for s, e in cls.frame_batches(num_frames, bs):
+            t = e - s
+            for _ in range(levels):
+                t = 1 + (t - 1) // 2 if t % 2 else t // 2
+            total += t
+        return total
+
     def _check_tiling(self, h, w, min_h, min_w):
         if self.use_tiling and (w > min_w or h > min_h):
             raise NotImplementedError(
