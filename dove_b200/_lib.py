@@ -37,7 +37,6 @@ _SIGS = {
     "dove_qk_norm_rope_bf16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
                                        c_void_p, c_void_p, c_int, c_void_p]),
     "dove_attention_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
-    "dove_attention_bf16_variant": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_void_p]),
     "dove_patchify_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "dove_unpatchify_velocity_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                               c_float, c_float, c_void_p]),
@@ -162,13 +161,10 @@ def qk_norm_rope(qkv, heads, q_w, q_b, k_w, k_b, eps, cos, sin, text_len):
     return qkv
 
 
-def attention(qkv, out, heads, scale, variant=None):
+def attention(qkv, out, heads, scale):
     rows = qkv.shape[0]
     assert qkv.shape[1] == 3 * heads * 64 and tuple(out.shape) == (rows, heads * 64)
-    if variant is None:
-        _call("dove_attention_bf16", _p(_bf16c(qkv)), _p(_bf16c(out)), rows, heads, scale, _stream())
-    else:
-        _call("dove_attention_bf16_variant", _p(_bf16c(qkv)), _p(_bf16c(out)), rows, heads, scale, variant, _stream())
+    _call("dove_attention_bf16", _p(_bf16c(qkv)), _p(_bf16c(out)), rows, heads, scale, _stream())
     return out
 
 

@@ -1,15 +1,19 @@
 // tcgen05 flash attention (non-causal, no mask) for the CogVideoX DiT: head_dim 64, q/k/v read straight from the
 // fused [rows, 3*heads*64] QKV buffer through one 2-D tensor map (no head-major re-layout).
 //
-// CTA = one 128-row query tile of one head; 192 threads:
-//   warp 0  TMA producer (Q once, then a ring of K/V tiles of 128 keys)
-//   warp 1  TMEM owner + single-thread MMA issuer:  S_j = Q K_j^T  (M128 N128 K64, both operands K-major smem)
-//                                                   PV_j = P_j V_j (M128 N64  K128, A = P from TMEM (or smem),
-//                                                                   B = V tile consumed MN-major as it sits)
-//   warps 2..5  softmax: one query row per thread (tcgen05.ld 32x32b), online max/sum in log2 domain, P packed to
-//               bf16 and written back to TMEM; the PV partial product of the previous tile is folded into the
-//               register accumulator O while the tensor core works on the current one.
-// TMEM columns: S[2] = 0..255, PV[2] = 256..383, P[2] = 384..511 (bf16 pairs).
+// CTA = one 128-row query tile of one head, 192 threads, TWO CTAs PER SM (80 KB smem, 256 TMEM columns each) so
+// that one CTA's softmax overlaps the other CTA's MMAs:
+//   warp 0      TMA producer (Q once, then a 2-stage ring of K/V tiles of 128 keys)
+//   warp 1      TMEM owner + single-thread MMA issuer:
+//                   S_j  = Q K_j^T      M128 N128 K64, both operands K-major smem (SW128)
+//                   O   += P_j V_j      M128 N64 K128, A = P from TMEM (bf16), B = V tile consumed MN-major
+//   warps 2..5  softmax, one query row per thread (tcgen05.ld 32x32b): single pass over the 128 S values held in
+//               registers, online max/sum in the log2 domain, P packed to bf16 and written to TMEM.
+// O accumulates in TMEM across all KV tiles.  Rescaling is LAZY: the running max used for the exponent is only
+// advanced when the true row max grew by more than 8 (log2 units), so O needs a TMEM read-modify-write only on
+// the rare tiles where that happens (P stays <= 2^8, well inside bf16/fp32 range); the final 1/l normalisation
+// uses the same stale max, so the result is exact softmax.
+// TMEM columns: S = 0..127, O = 128..191, P = 192..255 (bf16 pairs).
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -21,28 +25,32 @@ struct AttnParams {
   bf16* out;
 };
 
-constexpr int ATT_STAGES = 3;
+constexpr int ATT_STAGES = 2;
 constexpr uint32_t ATT_TILE_BYTES = 128 * 128;   // 128 rows x 64 bf16
-constexpr size_t ATT_SMEM = 1024 + ATT_TILE_BYTES * (1 + 2 * ATT_STAGES + 2 * 2) + 256;
+constexpr size_t ATT_SMEM = 1024 + ATT_TILE_BYTES * (1 + 2 * ATT_STAGES) + 128;
+constexpr float ATT_LAZY_THRESHOLD = 8.0f;
 
-template <bool kPTmem>
-__global__ void __launch_bounds__(192, 1)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(192, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + ATT_TILE_BYTES;
   uint8_t* sV = sK + ATT_STAGES * ATT_TILE_BYTES;
-  uint8_t* sP = sV + ATT_STAGES * ATT_TILE_BYTES;   // [2 buffers][2 k-halves][128 x 128 B] (smem-P variant only)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * ATT_TILE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ATT_STAGES * ATT_TILE_BYTES);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;
   uint64_t* kv_empty = kv_full + ATT_STAGES;
   uint64_t* s_full = kv_empty + ATT_STAGES;
-  uint64_t* p_full = s_full + 2;
-  uint64_t* o_full = p_full + 2;
-  uint64_t* o_empty = o_full + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_empty + 2);
+  uint64_t* p_full = s_full + 1;
+  uint64_t* pv_done = p_full + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pv_done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.y;
@@ -57,20 +65,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 4);
-      mbar_init(&o_full[i], 1);
-      mbar_init(&o_empty[i], 4);
-    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 4);
+    mbar_init(pv_done, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_ptr);
+  if (warp == 1) tmem_alloc<256>(tmem_ptr);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t TS = tmem_base, TO = tmem_base + 256, TP = tmem_base + 384;
+  const uint32_t TS = tmem_base, TO = tmem_base + 128, TP = tmem_base + 192;
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
@@ -91,154 +96,122 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // Q (K-major) x K (K-major)
-    constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);    // P (K-major / TMEM) x V (MN-major)
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);    // P (TMEM) x V (MN-major)
     const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ));
-    auto issue_s = [&](int j, int stage) {
+    auto issue_s = [&](int stage) {
       const uint64_t kdesc = umma_desc_sw128(smem_u32(sK + stage * ATT_TILE_BYTES));
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_ss(TS + (j & 1) * 128, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
-      umma_commit(&s_full[j & 1]);
+      for (int k = 0; k < 4; ++k) umma_ss(TS, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+      umma_commit(s_full);
     };
     mbar_wait(q_full, 0);
-    int stage_s = 0;
-    uint32_t phase_s = 0;   // ring position of the next tile whose S is to be issued
-    int stage_o = 0;        // ring position of tile j (PV)
     mbar_wait(&kv_full[0], 0);
     tc_fence_after();
-    issue_s(0, 0);
-    if (++stage_s == ATT_STAGES) { stage_s = 0; phase_s ^= 1; }
+    issue_s(0);
     for (int j = 0; j < nkv; ++j) {
-      const int b = j & 1;
-      const uint32_t ph2 = (j >> 1) & 1;
-      if (j + 1 < nkv) {
-        mbar_wait(&kv_full[stage_s], phase_s);
-        tc_fence_after();
-        issue_s(j + 1, stage_s);
-        if (++stage_s == ATT_STAGES) { stage_s = 0; phase_s ^= 1; }
-      }
-      mbar_wait(&p_full[b], ph2);
-      mbar_wait(&o_empty[b], ph2 ^ 1);
+      const int stage = j & 1;
+      mbar_wait(p_full, j & 1);
       tc_fence_after();
-      const uint64_t vdesc = umma_desc_sw128(smem_u32(sV + stage_o * ATT_TILE_BYTES));
+      const uint64_t vdesc = umma_desc_sw128(smem_u32(sV + stage * ATT_TILE_BYTES));
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {   // K = 128 keys, 16 per instruction: V advances 16 rows = 2048 B
-        if (kPTmem) {
-          umma_ts(TO + b * 64, TP + b * 64 + k * 8, vdesc + 128 * k, idesc_o, k != 0);
-        } else {
-          const uint64_t pdesc =
-              umma_desc_sw128(smem_u32(sP + (b * 2 + (k >> 2)) * ATT_TILE_BYTES)) + 2 * (k & 3);
-          umma_ss(TO + b * 64, pdesc, vdesc + 128 * k, idesc_o, k != 0);
-        }
+      for (int k = 0; k < 8; ++k)   // K = 128 keys, 16 per instruction: P +8 TMEM columns, V +16 rows = 2048 B
+        umma_ts(TO, TP + k * 8, vdesc + 128 * k, idesc_o, (j | k) != 0);
+      umma_commit(&kv_empty[stage]);
+      umma_commit(pv_done);
+      if (j + 1 < nkv) {
+        mbar_wait(&kv_full[stage ^ 1], ((j + 1) >> 1) & 1);
+        tc_fence_after();
+        issue_s(stage ^ 1);
       }
-      umma_commit(&kv_empty[stage_o]);
-      umma_commit(&o_full[b]);
-      if (++stage_o == ATT_STAGES) stage_o = 0;
     }
   } else if (warp >= 2) {
-    // ===================== softmax / accumulate =====================
+    // ===================== softmax =====================
     const int q = warp & 3;
     const int r = q * 32 + lane;            // query row in tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    float O[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) O[i] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
-
-    auto fold_pv = [&](int jb, uint32_t ph) {   // O = O*alpha_prev + PV[jb]
-      mbar_wait(&o_full[jb], ph);
-      tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld32(TO + lane_off + jb * 64 + c * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) O[c * 32 + i] = O[c * 32 + i] * alpha_prev + __uint_as_float(v[i]);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&o_empty[jb]);
-    };
+    float m_used = -INFINITY, l_run = 0.f;
+    const float sl2 = p.scale_log2;
 
     for (int j = 0; j < nkv; ++j) {
-      const int b = j & 1;
-      const uint32_t ph2 = (j >> 1) & 1;
-      mbar_wait(&s_full[b], ph2);
+      mbar_wait(s_full, j & 1);
       tc_fence_after();
-      const uint32_t ts = TS + lane_off + b * 128;
+      uint32_t v[128];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld32(TS + lane_off + c * 32, v + c * 32);
+      tmem_ld_wait();
       const int kbase = j * 128;
-      const bool tail = kbase + 128 > p.rows;
-      // pass 1: row max
+      if (kbase + 128 > p.rows) {            // tail tile: keys beyond `rows` are masked out
+#pragma unroll
+        for (int i = 0; i < 128; ++i)
+          if (kbase + i >= p.rows) v[i] = 0xff800000u;   // -inf
+      }
       float mx = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(ts + c * 32, v);
-        tmem_ld_wait();
+      for (int i = 0; i < 128; i += 2)
+        mx = fmaxf(mx, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+      const float m_new = fmaxf(m_used, mx * sl2);
+      const bool need = (m_new - m_used) > ATT_LAZY_THRESHOLD;     // first tile: inf > 8
+      const bool warp_need = __any_sync(0xffffffffu, need);
+      float alpha = 1.0f;
+      if (need) {
+        alpha = ex2_approx(m_used - m_new);
+        m_used = m_new;
+      }
+      if (j > 0) {
+        mbar_wait(pv_done, (j - 1) & 1);     // PV_{j-1} finished: P buffer is free, O is stable
+        tc_fence_after();
+        if (warp_need) {                     // rare after the first few tiles: O *= alpha (TMEM read-modify-write)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float s = __uint_as_float(v[i]);
-          if (tail && kbase + c * 32 + i >= p.rows) s = -INFINITY;
-          mx = fmaxf(mx, s);
+          for (int c = 0; c < 2; ++c) {
+            uint32_t o[32];
+            tmem_ld32(TO + lane_off + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(TO + lane_off + c * 32, o);
+          }
         }
       }
-      const float m_new = fmaxf(m_run, mx * p.scale_log2);
-      const float alpha = exp2f(m_run - m_new);
       float lsum = 0.f;
-      // pass 2: p = exp2(s*scale - m), pack to bf16, store
+      const float neg_m = -m_used;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(ts + c * 32, v);
-        tmem_ld_wait();
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float s0 = __uint_as_float(v[2 * i]) * p.scale_log2 - m_new;
-          float s1 = __uint_as_float(v[2 * i + 1]) * p.scale_log2 - m_new;
-          float p0 = exp2f(s0), p1 = exp2f(s1);
-          if (tail) {
-            if (kbase + c * 32 + 2 * i >= p.rows) p0 = 0.f;
-            if (kbase + c * 32 + 2 * i + 1 >= p.rows) p1 = 0.f;
-          }
+          const float p0 = ex2_approx(fmaf(__uint_as_float(v[c * 32 + 2 * i]), sl2, neg_m));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(v[c * 32 + 2 * i + 1]), sl2, neg_m));
           lsum += p0 + p1;
           pk[i] = pack_bf16x2(p0, p1);
         }
-        if (kPTmem) {
-          tmem_st16(TP + lane_off + b * 64 + c * 16, pk);
-        } else {
-          // K-major SW128 tile: row r, 16-byte chunk index (c*4+jj) within the 64-wide half (c >> 1)
-          uint8_t* base = sP + (b * 2 + (c >> 1)) * ATT_TILE_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            const int chunk = ((c & 1) * 4 + jj) ^ (r & 7);
-            *reinterpret_cast<uint4*>(base + chunk * 16) =
-                make_uint4(pk[jj * 4], pk[jj * 4 + 1], pk[jj * 4 + 2], pk[jj * 4 + 3]);
-          }
-        }
+        tmem_st16(TP + lane_off + c * 16, pk);
       }
-      if (kPTmem) tmem_st_wait(); else fence_proxy_async_smem();
+      tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[b]);
+      if (lane == 0) mbar_arrive(p_full);
       l_run = l_run * alpha + lsum;
-      if (j > 0) fold_pv(b ^ 1, ((j - 1) >> 1) & 1);
-      alpha_prev = alpha;
-      m_run = m_new;
     }
-    fold_pv((nkv - 1) & 1, ((nkv - 1) >> 1) & 1);
+    mbar_wait(pv_done, (nkv - 1) & 1);
+    tc_fence_after();
     const int row = q0 + r;
-    if (row < p.rows) {
-      const float inv = 1.0f / l_run;
-      uint4* op = reinterpret_cast<uint4*>(p.out + static_cast<long long>(row) * (p.heads * 64) + head * 64);
+    const float inv = 1.0f / l_run;
+    uint4* op = reinterpret_cast<uint4*>(p.out + static_cast<long long>(row) * (p.heads * 64) + head * 64);
 #pragma unroll
-      for (int jj = 0; jj < 8; ++jj) {
-        uint4 o;
-        o.x = pack_bf16x2(O[jj * 8 + 0] * inv, O[jj * 8 + 1] * inv);
-        o.y = pack_bf16x2(O[jj * 8 + 2] * inv, O[jj * 8 + 3] * inv);
-        o.z = pack_bf16x2(O[jj * 8 + 4] * inv, O[jj * 8 + 5] * inv);
-        o.w = pack_bf16x2(O[jj * 8 + 6] * inv, O[jj * 8 + 7] * inv);
-        op[jj] = o;
+    for (int c = 0; c < 2; ++c) {
+      uint32_t o[32];
+      tmem_ld32(TO + lane_off + c * 32, o);
+      tmem_ld_wait();
+      if (row < p.rows) {
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(o[jj * 8 + 0]) * inv, __uint_as_float(o[jj * 8 + 1]) * inv);
+          w.y = pack_bf16x2(__uint_as_float(o[jj * 8 + 2]) * inv, __uint_as_float(o[jj * 8 + 3]) * inv);
+          w.z = pack_bf16x2(__uint_as_float(o[jj * 8 + 4]) * inv, __uint_as_float(o[jj * 8 + 5]) * inv);
+          w.w = pack_bf16x2(__uint_as_float(o[jj * 8 + 6]) * inv, __uint_as_float(o[jj * 8 + 7]) * inv);
+          op[c * 4 + jj] = w;
+        }
       }
     }
   }
@@ -246,12 +219,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    tmem_dealloc<256>(tmem_base);
   }
 }
 
-static int attention_launch(const void* qkv, void* out, int rows, int heads, float scale, int variant,
-                            cudaStream_t st) {
+static int attention_launch(const void* qkv, void* out, int rows, int heads, float scale, cudaStream_t st) {
   if (int e = ensure_init()) return e;
   DOVE_CHECK_ARG(rows > 0 && heads > 0, "attention: empty problem");
   DOVE_CHECK_ARG(reinterpret_cast<uintptr_t>(qkv) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0,
@@ -268,18 +240,14 @@ static int attention_launch(const void* qkv, void* out, int rows, int heads, flo
   p.scale_log2 = scale * 1.4426950408889634f;
   p.out = static_cast<bf16*>(out);
   dim3 grid((rows + 127) / 128, heads);
-  cudaError_t e;
-  if (variant == 0) {
-    e = cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(ATT_SMEM));
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(ATT_SMEM));
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(attn)");
-    attn_fwd_kernel<true><<<grid, 192, ATT_SMEM, st>>>(tm, p);
-  } else {
-    e = cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(ATT_SMEM));
-    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(attn)");
-    attn_fwd_kernel<false><<<grid, 192, ATT_SMEM, st>>>(tm, p);
+    attr_set = true;
   }
+  attn_fwd_kernel<<<grid, 192, ATT_SMEM, st>>>(tm, p);
   DOVE_LAUNCH_CHECK("attn_fwd_kernel");
   return DOVE_OK;
 }
@@ -287,11 +255,5 @@ static int attention_launch(const void* qkv, void* out, int rows, int heads, flo
 }  // namespace dove
 
 extern "C" int dove_attention_bf16(const void* qkv, void* out, int rows, int heads, float scale, void* stream) {
-  return dove::attention_launch(qkv, out, rows, heads, scale, 0, static_cast<cudaStream_t>(stream));
-}
-
-// Test hook: variant 0 = P through TMEM (TS MMA), 1 = P through swizzled shared memory (SS MMA).
-extern "C" int dove_attention_bf16_variant(const void* qkv, void* out, int rows, int heads, float scale,
-                                           int variant, void* stream) {
-  return dove::attention_launch(qkv, out, rows, heads, scale, variant, static_cast<cudaStream_t>(stream));
+  return dove::attention_launch(qkv, out, rows, heads, scale, static_cast<cudaStream_t>(stream));
 }

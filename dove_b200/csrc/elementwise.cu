@@ -243,22 +243,32 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const bf16* __restrict_
   }
 }
 
+// one warp per group: lanes stride over the per-block partials (fixed order -> deterministic), fp64 combine
 __global__ void gn_finalize_kernel(const float* __restrict__ partial, int nblocks, int groups, double count,
                                    float eps, float* __restrict__ stats) {
-  const int g = threadIdx.x;
+  const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (g >= groups) return;
   double s = 0.0, q = 0.0;
-  for (int b = 0; b < nblocks; ++b) {
+  for (int b = lane; b < nblocks; b += 32) {
     s += partial[(static_cast<long long>(b) * groups + g) * 2];
     q += partial[(static_cast<long long>(b) * groups + g) * 2 + 1];
   }
-  const double mean = s / count;
-  double var = q / count - mean * mean;
-  if (var < 0.0) var = 0.0;
-  stats[g * 2] = static_cast<float>(mean);
-  stats[g * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if (lane == 0) {
+    const double mean = s / count;
+    double var = q / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[g * 2] = static_cast<float>(mean);
+    stats[g * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
 }
 
+// grid*block is a multiple of C/8, so every thread keeps ONE 8-channel column for its whole grid-stride loop and
+// the affine coefficients a = rstd*gamma, b = beta - mean*a are computed once per thread.
 __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int T,
                                                        int H, int W, int C, int groups,
                                                        const float* __restrict__ stats,
@@ -267,31 +277,40 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
                                                        const bf16* __restrict__ zb, int Tz, int hz, int wz) {
   const int vcols = C >> 3;
   const int cpg = C / groups;
-  const long long nvec = static_cast<long long>(T) * H * W * vcols;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int vcol = static_cast<int>(i % vcols);
-    const long long vox = i / vcols;
-    const int c0 = vcol * 8;
-    float f[8], g[8], bt[8];
-    unpack8(*reinterpret_cast<const uint4*>(x + i * 8), f);
+  const int vcol = threadIdx.x % vcols;
+  const int c0 = vcol * 8;
+  float a[8], b[8];
+  {
+    float g[8], bt[8];
     unpack8(*reinterpret_cast<const uint4*>(gamma + c0), g);
     unpack8(*reinterpret_cast<const uint4*>(beta + c0), bt);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int grp = (c0 + k) / cpg;
       const float mean = stats[grp * 2], rstd = stats[grp * 2 + 1];
-      const float a = rstd * g[k];
-      f[k] = bf16_round(f[k] * a + (bt[k] - mean * a));
+      a[k] = rstd * g[k];
+      b[k] = bt[k] - mean * a[k];
     }
+  }
+  const long long nvox = static_cast<long long>(T) * H * W;
+  const int vper = blockDim.x / vcols;
+  const long long HW = static_cast<long long>(H) * W;
+  for (long long vox = static_cast<long long>(blockIdx.x) * vper + threadIdx.x / vcols; vox < nvox;
+       vox += static_cast<long long>(gridDim.x) * vper) {
+    const long long i = vox * vcols + vcol;
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(x + i * 8), f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = bf16_round(f[k] * a[k] + b[k]);
     if (zy) {
-      const int xw = static_cast<int>(vox % W), yh = static_cast<int>((vox / W) % H);
-      const int tf = static_cast<int>(vox / (static_cast<long long>(W) * H));
+      const int tf = static_cast<int>(vox / HW);
+      const int rem = static_cast<int>(vox - tf * HW);
+      const int yh = rem / W, xw = rem - yh * W;
       int tz;
-      if (T > 1 && (T & 1)) tz = (tf == 0) ? 0 : 1 + static_cast<int>((static_cast<long long>(tf - 1) * (Tz - 1)) / (T - 1));
-      else tz = static_cast<int>((static_cast<long long>(tf) * Tz) / T);
-      const int yz = static_cast<int>((static_cast<long long>(yh) * hz) / H);
-      const int xz = static_cast<int>((static_cast<long long>(xw) * wz) / W);
+      if (T > 1 && (T & 1)) tz = (tf == 0) ? 0 : 1 + ((tf - 1) * (Tz - 1)) / (T - 1);
+      else tz = (tf * Tz) / T;
+      const int yz = (yh * hz) / H;
+      const int xz = (xw * wz) / W;
       const long long zoff = ((static_cast<long long>(tz) * hz + yz) * wz + xz) * C + c0;
       float yv[8], bv[8];
       unpack8(*reinterpret_cast<const uint4*>(zy + zoff), yv);
@@ -518,7 +537,7 @@ extern "C" int dove_gn_stats_bf16(const void* x, int64_t nvox, int C, int groups
   gn_partial_kernel<<<static_cast<int>(blocks), 256, 0, ST(stream)>>>(static_cast<const bf16*>(x), nvox, C, groups,
                                                                     partial);
   DOVE_LAUNCH_CHECK("gn_partial_kernel");
-  gn_finalize_kernel<<<1, 32, 0, ST(stream)>>>(partial, static_cast<int>(blocks), groups,
+  gn_finalize_kernel<<<1, 32 * 32, 0, ST(stream)>>>(partial, static_cast<int>(blocks), groups,
                                               static_cast<double>(nvox) * (C / groups), eps, stats);
   DOVE_LAUNCH_CHECK("gn_finalize_kernel");
   return DOVE_OK;
@@ -530,8 +549,9 @@ extern "C" int dove_gn_apply_bf16(const void* x, void* out, int T, int H, int W,
   if (int e = ensure_init()) return e;
   DOVE_CHECK_ARG(T > 0 && H > 0 && W > 0 && C % 8 == 0 && C % groups == 0, "gn_apply: bad shape");
   DOVE_CHECK_ARG((zq_y == nullptr) == (zq_b == nullptr), "gn_apply: zq_y/zq_b must come together");
+  DOVE_CHECK_ARG(256 % (C >> 3) == 0, "gn_apply: C/8 must divide 256 (C=%d)", C);
   const long long nvec = static_cast<long long>(T) * H * W * (C >> 3);
-  gn_apply_kernel<<<grid_for(nvec, 256), 256, 0, ST(stream)>>>(
+  gn_apply_kernel<<<grid_for(nvec, 256, 8), 256, 0, ST(stream)>>>(
       static_cast<const bf16*>(x), static_cast<bf16*>(out), T, H, W, C, groups, stats,
       static_cast<const bf16*>(gamma), static_cast<const bf16*>(beta), apply_silu, static_cast<const bf16*>(zq_y),
       static_cast<const bf16*>(zq_b), Tz, hz, wz);

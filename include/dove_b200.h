@@ -80,7 +80,7 @@ int dove_qk_norm_rope_bf16(void* qkv, int rows, int heads, const void* q_w, cons
                            void* stream);
 
 /* out[rows, heads*64] = softmax(q k^T / 8) v per head, non-causal, no mask.  q,k,v read from the fused
- * qkv [rows, 3*heads*64] buffer.  tcgen05 flash-attention kernel (S and P in TMEM).
+ * qkv [rows, 3*heads*64] buffer.  tcgen05 flash-attention kernel (S, P and O in TMEM, lazy rescaling).
  * F.scaled_dot_product_attention in CogVideoXAttnProcessor2_0. */
 int dove_attention_bf16(const void* qkv, void* out, int rows, int heads, float scale, void* stream);
 
@@ -97,11 +97,6 @@ int dove_unpatchify_velocity_bf16(const void* tokens, const void* latent, void* 
 /* out = bf16(bf16(a*noise) - bf16(b*sample)) — CogVideoXDPMScheduler.get_velocity(sample, noise, t) standalone
  * (the call-surface path; the fused path uses dove_unpatchify_velocity_bf16). */
 int dove_velocity_bf16(const void* sample, const void* noise, void* out, int64_t n, float a, float b, void* stream);
-
-/* Test hook for the two P-operand paths of the attention kernel: variant 0 = P through TMEM (shipping path),
- * 1 = P through swizzled shared memory. */
-int dove_attention_bf16_variant(const void* qkv, void* out, int rows, int heads, float scale, int variant,
-                                void* stream);
 
 /* ---- VAE (channels-last) ---------------------------------------------------------------------------------- */
 

@@ -126,19 +126,18 @@ def test_conv_planar_out(L):
     assert rel_l2(y, rb(ref)) < TOL
 
 
-@pytest.mark.parametrize("variant", [0, 1])
-@pytest.mark.parametrize("rows,heads", [(128, 1), (200, 2), (482, 3), (1000, 2), (2304, 4)])
-def test_attention(L, rows, heads, variant):
+@pytest.mark.parametrize("rows,heads", [(128, 1), (200, 2), (482, 3), (1000, 2), (2304, 4), (19426, 2)])
+def test_attention(L, rows, heads):
     qkv = randn(rows, 3 * heads * 64, seed=rows)
     out = torch.full((rows, heads * 64), float("nan"), device="cuda", dtype=torch.bfloat16)
-    L.attention(qkv, out, heads, 0.125, variant=variant)
+    L.attention(qkv, out, heads, 0.125)
     torch.cuda.synchronize()
     q, k, v = [t.float().reshape(rows, heads, 64).transpose(0, 1) for t in qkv.chunk(3, dim=1)]
     p = torch.softmax(q @ k.transpose(1, 2) * 0.125, dim=-1)
     ref = (p @ v).transpose(0, 1).reshape(rows, heads * 64)
-    assert torch.isfinite(out.float()).all(), f"variant {variant}: non-finite output"
+    assert torch.isfinite(out.float()).all()
     e = rel_l2(out, ref)
-    print(f"attention rows{rows} heads{heads} variant{variant}: rel_l2={e:.3e}")
+    print(f"attention rows{rows} heads{heads}: rel_l2={e:.3e}")
     assert e < 5e-3    # P is rounded to bf16 before the PV matmul (as flash SDPA does)
 
 
