@@ -110,19 +110,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
     issue_s(0);
     for (int j = 0; j < nkv; ++j) {
       const int stage = j & 1;
-      mbar_wait(p_full, j & 1);
+      mbar_wait(p_full, j & 1);            // softmax_j has read all of S_j and written P_j
       tc_fence_after();
+      if (j + 1 < nkv) {                   // S_{j+1} first: softmax_{j+1} can start while PV_j runs
+        mbar_wait(&kv_full[stage ^ 1], ((j + 1) >> 1) & 1);
+        tc_fence_after();
+        issue_s(stage ^ 1);
+      }
       const uint64_t vdesc = umma_desc_sw128(smem_u32(sV + stage * ATT_TILE_BYTES));
 #pragma unroll
       for (int k = 0; k < 8; ++k)   // K = 128 keys, 16 per instruction: P +8 TMEM columns, V +16 rows = 2048 B
         umma_ts(TO, TP + k * 8, vdesc + 128 * k, idesc_o, (j | k) != 0);
       umma_commit(&kv_empty[stage]);
       umma_commit(pv_done);
-      if (j + 1 < nkv) {
-        mbar_wait(&kv_full[stage ^ 1], ((j + 1) >> 1) & 1);
-        tc_fence_after();
-        issue_s(stage ^ 1);
-      }
     }
   } else if (warp >= 2) {
     // ===================== softmax =====================
@@ -145,10 +145,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
         for (int i = 0; i < 128; ++i)
           if (kbase + i >= p.rows) v[i] = 0xff800000u;   // -inf
       }
-      float mx = -INFINITY;
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // 4 independent chains (ILP)
 #pragma unroll
-      for (int i = 0; i < 128; i += 2)
-        mx = fmaxf(mx, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+      for (int i = 0; i < 128; i += 8) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          mx4[u] = fmaxf(mx4[u], fmaxf(__uint_as_float(v[i + 2 * u]), __uint_as_float(v[i + 2 * u + 1])));
+      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float m_new = fmaxf(m_used, mx * sl2);
       const bool need = (m_new - m_used) > ATT_LAZY_THRESHOLD;     // first tile: inf > 8
       const bool warp_need = __any_sync(0xffffffffu, need);
@@ -157,8 +161,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
         alpha = ex2_approx(m_used - m_new);
         m_used = m_new;
       }
+      // exponentials first (MUFU-bound phase, overlaps PV_{j-1} still running on the tensor pipe) ...
+      float lsum = 0.f;
+      const float neg_m = -m_used;
+      uint32_t pk[64];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), sl2, neg_m));
+        const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), sl2, neg_m));
+        lsum += p0 + p1;
+        pk[i] = pack_bf16x2(p0, p1);
+      }
+      // ... then wait for PV_{j-1}: the P buffer is free and O is stable from here on
       if (j > 0) {
-        mbar_wait(pv_done, (j - 1) & 1);     // PV_{j-1} finished: P buffer is free, O is stable
+        mbar_wait(pv_done, (j - 1) & 1);
         tc_fence_after();
         if (warp_need) {                     // rare after the first few tiles: O *= alpha (TMEM read-modify-write)
 #pragma unroll
@@ -172,20 +188,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
           }
         }
       }
-      float lsum = 0.f;
-      const float neg_m = -m_used;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(v[c * 32 + 2 * i]), sl2, neg_m));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(v[c * 32 + 2 * i + 1]), sl2, neg_m));
-          lsum += p0 + p1;
-          pk[i] = pack_bf16x2(p0, p1);
-        }
-        tmem_st16(TP + lane_off + c * 16, pk);
-      }
+      for (int c = 0; c < 4; ++c) tmem_st16(TP + lane_off + c * 16, pk + c * 16);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();

@@ -10,7 +10,7 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
   float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
   f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
@@ -295,34 +295,47 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
   const long long nvox = static_cast<long long>(T) * H * W;
   const int vper = blockDim.x / vcols;
   const long long HW = static_cast<long long>(H) * W;
-  for (long long vox = static_cast<long long>(blockIdx.x) * vper + threadIdx.x / vcols; vox < nvox;
-       vox += static_cast<long long>(gridDim.x) * vper) {
-    const long long i = vox * vcols + vcol;
-    float f[8];
-    unpack8(*reinterpret_cast<const uint4*>(x + i * 8), f);
+  const long long stride = static_cast<long long>(gridDim.x) * vper;
+  constexpr int U = 4;                       // voxels in flight per thread (memory-level parallelism)
+  for (long long vox0 = static_cast<long long>(blockIdx.x) * vper + threadIdx.x / vcols; vox0 < nvox;
+       vox0 += stride * U) {
+    uint4 raw[U];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) f[k] = bf16_round(f[k] * a[k] + b[k]);
-    if (zy) {
-      const int tf = static_cast<int>(vox / HW);
-      const int rem = static_cast<int>(vox - tf * HW);
-      const int yh = rem / W, xw = rem - yh * W;
-      int tz;
-      if (T > 1 && (T & 1)) tz = (tf == 0) ? 0 : 1 + ((tf - 1) * (Tz - 1)) / (T - 1);
-      else tz = (tf * Tz) / T;
-      const int yz = (yh * hz) / H;
-      const int xz = (xw * wz) / W;
-      const long long zoff = ((static_cast<long long>(tz) * hz + yz) * wz + xz) * C + c0;
-      float yv[8], bv[8];
-      unpack8(*reinterpret_cast<const uint4*>(zy + zoff), yv);
-      unpack8(*reinterpret_cast<const uint4*>(zb + zoff), bv);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) f[k] = bf16_round(bf16_round(f[k] * yv[k]) + bv[k]);
+    for (int u = 0; u < U; ++u) {
+      const long long vox = vox0 + u * stride;
+      if (vox < nvox) raw[u] = *reinterpret_cast<const uint4*>(x + (vox * vcols + vcol) * 8);
     }
-    if (apply_silu) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) f[k] = silu_f(f[k]);
+    for (int u = 0; u < U; ++u) {
+      const long long vox = vox0 + u * stride;
+      if (vox >= nvox) break;
+      const long long i = vox * vcols + vcol;
+      float f[8];
+      unpack8(raw[u], f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = bf16_round(f[k] * a[k] + b[k]);
+      if (zy) {
+        const int tf = static_cast<int>(vox / HW);
+        const int rem = static_cast<int>(vox - tf * HW);
+        const int yh = rem / W, xw = rem - yh * W;
+        int tz;
+        if (T > 1 && (T & 1)) tz = (tf == 0) ? 0 : 1 + ((tf - 1) * (Tz - 1)) / (T - 1);
+        else tz = (tf * Tz) / T;
+        const int yz = (yh * hz) / H;
+        const int xz = (xw * wz) / W;
+        const long long zoff = ((static_cast<long long>(tz) * hz + yz) * wz + xz) * C + c0;
+        float yv[8], bv[8];
+        unpack8(*reinterpret_cast<const uint4*>(zy + zoff), yv);
+        unpack8(*reinterpret_cast<const uint4*>(zb + zoff), bv);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = bf16_round(bf16_round(f[k] * yv[k]) + bv[k]);
+      }
+      if (apply_silu) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = silu_f(f[k]);
+      }
+      *reinterpret_cast<uint4*>(out + i * 8) = pack8(f);
     }
-    *reinterpret_cast<uint4*>(out + i * 8) = pack8(f);
   }
 }
 

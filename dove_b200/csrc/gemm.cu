@@ -5,8 +5,9 @@
 // tap, the shifted [th x tw x 64ch] window of the activation tensor (4-D tensor map, OOB zero fill = spatial
 // zero padding) — no im2col buffer ever exists.
 //
-// CTA = 192 threads: warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
-// warps 2..5 = epilogue (TMEM -> registers -> fused epilogue -> global).  Accumulators are double-buffered in
+// CTA = 320 threads: warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
+// warps 2..9 = epilogue (TMEM -> registers -> fused epilogue -> global; two warps per TMEM lane quarter, each
+// taking every other 32-column chunk, so the epilogue has 2 warps per SMSP to hide its own latencies).  Accumulators are double-buffered in
 // TMEM (2 x BN fp32 columns) so the epilogue of tile i overlaps the main loop of tile i+1.
 #include "common.cuh"
 #include "ptx.cuh"
@@ -40,7 +41,7 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
   // 0.5*x*(1+tanh(sqrt(2/pi)*(x+0.044715x^3))), tanh(y) = 1 - 2/(exp(2y)+1)
   const float kBeta = 0.7978845608028654f, kKappa = 0.044715f;
   float inner = kBeta * (x + kKappa * x * x * x);
-  float t = 1.0f - 2.0f / (__expf(2.0f * inner) + 1.0f);
+  float t = 1.0f - __fdividef(2.0f, __expf(2.0f * inner) + 1.0f);
   return 0.5f * x * (1.0f + t);
 }
 
@@ -56,7 +57,7 @@ struct GemmCfg {
 };
 
 template <int BN, bool kConv>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
   using Cfg = GemmCfg<BN>;
@@ -85,7 +86,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], 8);
     }
     fence_mbar_init();
   }
@@ -162,6 +163,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp >= 2) {
     // ===================== epilogue warps =====================
     const int q = warp & 3;               // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;     // two warps per quarter: even / odd column chunks
     const int r_in_tile = q * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -186,36 +188,51 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
       const bf16* gate = (p.epi == DOVE_EPI_GATED_RES) ? (row < p.split_row ? p.gate0 : p.gate1) : nullptr;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += CH) {
+      for (int c0 = half * CH; c0 < BN; c0 += 2 * CH) {
         uint32_t v[CH];
         if (CH == 32) tmem_ld32(t_row + c0, v); else tmem_ld16(t_row + c0, v);
         tmem_ld_wait();
         const int n0 = nt * BN + c0;
         if (valid) {
           float r[CH];
+          if (p.bias) {
+            const uint4* bp = reinterpret_cast<const uint4*>(p.bias + n0);
 #pragma unroll
-          for (int i = 0; i < CH; ++i) {
-            float x = __uint_as_float(v[i]);
-            if (p.bias) x += __bfloat162float(p.bias[n0 + i]);
-            r[i] = bf16_round(x);
+            for (int j = 0; j < CH / 8; ++j) {
+              const uint4 b4 = bp[j];
+              const uint32_t bu[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float2 b2 = unpack_bf16x2(bu[k]);
+                r[j * 8 + 2 * k] = bf16_round(__uint_as_float(v[j * 8 + 2 * k]) + b2.x);
+                r[j * 8 + 2 * k + 1] = bf16_round(__uint_as_float(v[j * 8 + 2 * k + 1]) + b2.y);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < CH; ++i) r[i] = bf16_round(__uint_as_float(v[i]));
           }
           if (p.epi == DOVE_EPI_GELU_TANH) {
 #pragma unroll
             for (int i = 0; i < CH; ++i) r[i] = gelu_tanh_f(r[i]);
           } else if (p.epi == DOVE_EPI_GATED_RES || p.epi == DOVE_EPI_ADD) {
             const uint4* ap = reinterpret_cast<const uint4*>(p.aux + row * p.ld_aux + n0);
+            const uint4* gp = reinterpret_cast<const uint4*>((gate ? gate : p.aux) + n0);
 #pragma unroll
             for (int j = 0; j < CH / 8; ++j) {
               const uint4 a4 = ap[j];
               const uint32_t au[4] = {a4.x, a4.y, a4.z, a4.w};
+              uint4 g4 = make_uint4(0, 0, 0, 0);
+              if (p.epi == DOVE_EPI_GATED_RES) g4 = gp[j];
+              const uint32_t gu[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const float2 a2 = unpack_bf16x2(au[k]);
                 const int i = j * 8 + k * 2;
                 if (p.epi == DOVE_EPI_GATED_RES) {
-                  const float g0 = __bfloat162float(gate[n0 + i]), g1 = __bfloat162float(gate[n0 + i + 1]);
-                  r[i] = a2.x + bf16_round(g0 * r[i]);
-                  r[i + 1] = a2.y + bf16_round(g1 * r[i + 1]);
+                  const float2 g2 = unpack_bf16x2(gu[k]);
+                  r[i] = a2.x + bf16_round(g2.x * r[i]);
+                  r[i + 1] = a2.y + bf16_round(g2.y * r[i + 1]);
                 } else {
                   r[i] += a2.x;
                   r[i + 1] += a2.y;
@@ -273,7 +290,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   }
   const int total = p.num_m_tiles * p.num_n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
-  umma_gemm_kernel<BN, kConv><<<grid, 192, Cfg::SMEM, st>>>(tmA, tmB, p);
+  umma_gemm_kernel<BN, kConv><<<grid, 320, Cfg::SMEM, st>>>(tmA, tmB, p);
   DOVE_LAUNCH_CHECK("umma_gemm_kernel");
   return DOVE_OK;
 }
