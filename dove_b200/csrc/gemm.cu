@@ -19,6 +19,7 @@ struct GemmParams {
   int M;   // dense: valid rows
   // conv geometry
   int tw, th, tiles_w, tiles_h;
+  int band_h, To;   // L2-friendly tile order: bands of band_h tile-rows, all To frames of a band before the next
   int Ho, Wo;
   int kh, kw, cin_blocks;
   int stride, pad;
@@ -43,6 +44,21 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
   float inner = kBeta * (x + kKappa * x * x * x);
   float t = 1.0f - __fdividef(2.0f, __expf(2.0f * inner) + 1.0f);
   return 0.5f * x * (1.0f + t);
+}
+
+// conv m-tile index -> (frame t, tile row hy, tile col wx).  Tiles are ordered band-major: a band is `band_h` tile
+// rows; within a band all frames are visited before moving on, so the 3 output frames that share an input
+// frame (and the 3 tile rows that share an input row) are processed while that input is still in L2.
+__device__ __forceinline__ void conv_tile_coords(const GemmParams& p, int mt, int& t, int& hy, int& wx) {
+  const int full_band = p.band_h * p.tiles_w * p.To;
+  const int b = mt / full_band;
+  const int r = mt - b * full_band;
+  const int gb = min(p.band_h, p.tiles_h - b * p.band_h);
+  const int pb = gb * p.tiles_w;
+  t = r / pb;
+  const int rr = r - t * pb;
+  hy = b * p.band_h + rr / p.tiles_w;
+  wx = rr % p.tiles_w;
 }
 
 template <int BN>
@@ -104,11 +120,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int mt = tile / p.num_n_tiles, nt = tile % p.num_n_tiles;
       int t = 0, h0 = 0, w0 = 0;
       if (kConv) {
-        const int tpf = p.tiles_h * p.tiles_w;
-        t = mt / tpf;
-        const int r = mt - t * tpf;
-        h0 = (r / p.tiles_w) * p.th;
-        w0 = (r % p.tiles_w) * p.tw;
+        int hy, wx;
+        conv_tile_coords(p, mt, t, hy, wx);
+        h0 = hy * p.th;
+        w0 = wx * p.tw;
       }
       for (int kb = 0; kb < p.num_kb; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1);
@@ -172,11 +187,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       long long row;
       bool valid;
       if (kConv) {
-        const int tpf = p.tiles_h * p.tiles_w;
-        const int t = mt / tpf;
-        const int r = mt - t * tpf;
-        const int h = (r / p.tiles_w) * p.th + r_in_tile / p.tw;
-        const int w = (r % p.tiles_w) * p.tw + r_in_tile % p.tw;
+        int t, hy, wx;
+        conv_tile_coords(p, mt, t, hy, wx);
+        const int h = hy * p.th + r_in_tile / p.tw;
+        const int w = wx * p.tw + r_in_tile % p.tw;
         valid = (h < p.Ho) && (w < p.Wo);
         row = (static_cast<long long>(t) * p.Ho + h) * p.Wo + w;
       } else {
@@ -420,6 +434,14 @@ extern "C" int dove_conv_cl_bf16(const void* x, const void* w, const void* bias,
   p.tiles_w = (Wo + tw - 1) / tw;
   p.tiles_h = (Ho + th - 1) / th;
   p.num_m_tiles = Tout * p.tiles_w * p.tiles_h;
+  p.To = Tout;
+  {   // band height: keep (band rows + halo) x all input frames of the band within ~32 MB of L2
+    const double row_bytes = static_cast<double>(Win) * Cin * 2.0 * Tin * th * stride;
+    int bh = static_cast<int>(32.0e6 / row_bytes);
+    if (bh < 1) bh = 1;
+    if (bh > p.tiles_h) bh = p.tiles_h;
+    p.band_h = bh;
+  }
   p.num_n_tiles = Cout_pad / bn;
   p.num_kb = Ktot / 64;
   p.Ho = Ho;
