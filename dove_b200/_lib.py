@@ -29,6 +29,7 @@ _SIGS = {
     "dove_init": (c_int, [c_int]),
     "dove_last_error": (c_char_p, []),
     "dove_num_sms": (c_int, []),
+    "dove_set_option": (c_int, [c_char_p, c_int]),
     "dove_gemm_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int,
                                c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p]),
     "dove_gemv_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
@@ -94,6 +95,12 @@ def init(device: int | None = None) -> None:
     if rc != 0:
         raise DoveError(f"dove_init({device}) failed ({rc}): {lib.dove_last_error().decode()}")
     _inited_device = device
+
+
+def set_option(name: str, value: int) -> None:
+    rc = load().dove_set_option(name.encode(), int(value))
+    if rc != 0:
+        raise DoveError(load().dove_last_error().decode())
 
 
 def _p(t):

@@ -4,6 +4,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
 #include <cudaTypedefs.h>
 
 namespace dove {
@@ -27,6 +28,9 @@ int check_cuda(cudaError_t e, const char* what) {
 }
 
 int num_sms() { return g_num_sms; }
+
+static int g_opt_conv2cta = 1;
+int get_option_conv2cta() { return g_opt_conv2cta; }
 
 int ensure_init() {
   if (g_device < 0) return set_error(DOVE_E_NOT_INIT, "dove_init(device) has not been called");
@@ -59,6 +63,14 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 }  // namespace dove
 
 using namespace dove;
+
+extern "C" int dove_set_option(const char* name, int value) {
+  if (name && !strcmp(name, "conv2cta")) {
+    g_opt_conv2cta = value;
+    return DOVE_OK;
+  }
+  return set_error(DOVE_E_BAD_ARG, "unknown option %s", name ? name : "(null)");
+}
 
 extern "C" int dove_abi_version(void) { return DOVE_ABI_VERSION; }
 

@@ -9,57 +9,13 @@
 // warps 2..9 = epilogue (TMEM -> registers -> fused epilogue -> global; two warps per TMEM lane quarter, each
 // taking every other 32-column chunk, so the epilogue has 2 warps per SMSP to hide its own latencies).  Accumulators are double-buffered in
 // TMEM (2 x BN fp32 columns) so the epilogue of tile i overlaps the main loop of tile i+1.
-#include "common.cuh"
-#include "ptx.cuh"
+#include "gemm_common.cuh"
 
 namespace dove {
 
-struct GemmParams {
-  int num_m_tiles, num_n_tiles, num_kb;
-  int M;   // dense: valid rows
-  // conv geometry
-  int tw, th, tiles_w, tiles_h;
-  int band_h, To;   // L2-friendly tile order: bands of band_h tile-rows, all To frames of a band before the next
-  int Ho, Wo;
-  int kh, kw, cin_blocks;
-  int stride, pad;
-  // epilogue
-  int epi;
-  bf16* C;
-  long long ldc;
-  const bf16* bias;
-  const bf16* aux;
-  long long ld_aux;
-  const bf16* gate0;
-  const bf16* gate1;
-  int split_row;
-  int n_valid;    // columns stored
-  int out_mode;   // 0 row-major [rows, ldc], 1 planar [n][rows_total]
-  long long rows_total;
-};
-
-__device__ __forceinline__ float gelu_tanh_f(float x) {
-  // 0.5*x*(1+tanh(sqrt(2/pi)*(x+0.044715x^3))), tanh(y) = 1 - 2/(exp(2y)+1)
-  const float kBeta = 0.7978845608028654f, kKappa = 0.044715f;
-  float inner = kBeta * (x + kKappa * x * x * x);
-  float t = 1.0f - __fdividef(2.0f, __expf(2.0f * inner) + 1.0f);
-  return 0.5f * x * (1.0f + t);
-}
-
-// conv m-tile index -> (frame t, tile row hy, tile col wx).  Tiles are ordered band-major: a band is `band_h` tile
-// rows; within a band all frames are visited before moving on, so the 3 output frames that share an input
-// frame (and the 3 tile rows that share an input row) are processed while that input is still in L2.
-__device__ __forceinline__ void conv_tile_coords(const GemmParams& p, int mt, int& t, int& hy, int& wx) {
-  const int full_band = p.band_h * p.tiles_w * p.To;
-  const int b = mt / full_band;
-  const int r = mt - b * full_band;
-  const int gb = min(p.band_h, p.tiles_h - b * p.band_h);
-  const int pb = gb * p.tiles_w;
-  t = r / pb;
-  const int rr = r - t * pb;
-  hy = b * p.band_h + rr / p.tiles_w;
-  wx = rr % p.tiles_w;
-}
+int conv2cta_dispatch(const void* x, const void* w, int Tout, int Hin, int Win, int Cin, int Cout_pad, int kt,
+                      int Ho, int Wo, GemmParams p, cudaStream_t st);
+int get_option_conv2cta();
 
 template <int BN>
 struct GemmCfg {
@@ -208,73 +164,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tmem_ld_wait();
         const int n0 = nt * BN + c0;
         if (valid) {
-          float r[CH];
-          if (p.bias) {
-            const uint4* bp = reinterpret_cast<const uint4*>(p.bias + n0);
-#pragma unroll
-            for (int j = 0; j < CH / 8; ++j) {
-              const uint4 b4 = bp[j];
-              const uint32_t bu[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const float2 b2 = unpack_bf16x2(bu[k]);
-                r[j * 8 + 2 * k] = bf16_round(__uint_as_float(v[j * 8 + 2 * k]) + b2.x);
-                r[j * 8 + 2 * k + 1] = bf16_round(__uint_as_float(v[j * 8 + 2 * k + 1]) + b2.y);
-              }
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < CH; ++i) r[i] = bf16_round(__uint_as_float(v[i]));
-          }
-          if (p.epi == DOVE_EPI_GELU_TANH) {
-#pragma unroll
-            for (int i = 0; i < CH; ++i) r[i] = gelu_tanh_f(r[i]);
-          } else if (p.epi == DOVE_EPI_GATED_RES || p.epi == DOVE_EPI_ADD) {
-            const uint4* ap = reinterpret_cast<const uint4*>(p.aux + row * p.ld_aux + n0);
-            const uint4* gp = reinterpret_cast<const uint4*>((gate ? gate : p.aux) + n0);
-#pragma unroll
-            for (int j = 0; j < CH / 8; ++j) {
-              const uint4 a4 = ap[j];
-              const uint32_t au[4] = {a4.x, a4.y, a4.z, a4.w};
-              uint4 g4 = make_uint4(0, 0, 0, 0);
-              if (p.epi == DOVE_EPI_GATED_RES) g4 = gp[j];
-              const uint32_t gu[4] = {g4.x, g4.y, g4.z, g4.w};
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const float2 a2 = unpack_bf16x2(au[k]);
-                const int i = j * 8 + k * 2;
-                if (p.epi == DOVE_EPI_GATED_RES) {
-                  const float2 g2 = unpack_bf16x2(gu[k]);
-                  r[i] = a2.x + bf16_round(g2.x * r[i]);
-                  r[i + 1] = a2.y + bf16_round(g2.y * r[i + 1]);
-                } else {
-                  r[i] += a2.x;
-                  r[i + 1] += a2.y;
-                }
-              }
-            }
-          }
-          if (p.out_mode == 0 && n0 + CH <= p.n_valid) {
-            uint4* cp = reinterpret_cast<uint4*>(p.C + row * p.ldc + n0);
-#pragma unroll
-            for (int j = 0; j < CH / 8; ++j) {
-              uint4 o;
-              o.x = pack_bf16x2(r[j * 8 + 0], r[j * 8 + 1]);
-              o.y = pack_bf16x2(r[j * 8 + 2], r[j * 8 + 3]);
-              o.z = pack_bf16x2(r[j * 8 + 4], r[j * 8 + 5]);
-              o.w = pack_bf16x2(r[j * 8 + 6], r[j * 8 + 7]);
-              cp[j] = o;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < CH; ++i) {
-              const int n = n0 + i;
-              if (n < p.n_valid) {
-                if (p.out_mode == 0) p.C[row * p.ldc + n] = __float2bfloat16_rn(r[i]);
-                else p.C[static_cast<long long>(n) * p.rows_total + row] = __float2bfloat16_rn(r[i]);
-              }
-            }
-          }
+          epilogue_chunk<CH>(p, v, row, n0, gate);
         }
       }
       tc_fence_before();
@@ -396,6 +286,29 @@ extern "C" int dove_conv_cl_bf16(const void* x, const void* w, const void* bias,
   if (out_mode == 0) DOVE_CHECK_ARG(ldy % 8 == 0, "conv: ldy must be a multiple of 8");
   if (out_mode == 1) DOVE_CHECK_ARG(ldy >= static_cast<long long>(Tout) * Ho * Wo, "conv: planar plane stride too small");
   if (epilogue == DOVE_EPI_ADD) DOVE_CHECK_ARG(aux && ld_aux % 8 == 0, "conv: add epilogue needs aux");
+  {   // CTA-pair kernel with in-smem reuse of the W taps for the big stride-1 3x3(x3) convs on wide images
+    const int opt = get_option_conv2cta();
+    if (opt != 0 && stride == 1 && kh == 3 && kw == 3 && pad == 1 && out_mode == 0 && Wo >= 256 && Hin == Ho &&
+        Win == Wo && (Cout_pad == 128 || Cout_pad % 256 == 0) && cout_valid == Cout_pad) {
+      GemmParams q{};
+      q.Ho = Ho;
+      q.Wo = Wo;
+      q.kh = kh;
+      q.kw = kw;
+      q.stride = 1;
+      q.pad = 1;
+      q.epi = epilogue;
+      q.C = static_cast<bf16*>(y);
+      q.ldc = ldy;
+      q.bias = static_cast<const bf16*>(bias);
+      q.aux = static_cast<const bf16*>(aux);
+      q.ld_aux = ld_aux;
+      q.n_valid = cout_valid;
+      q.out_mode = 0;
+      q.rows_total = static_cast<long long>(Tout) * Ho * Wo;
+      return conv2cta_dispatch(x, w, Tout, Hin, Win, Cin, Cout_pad, kt, Ho, Wo, q, static_cast<cudaStream_t>(stream));
+    }
+  }
   const int bn = pick_bn(Cout_pad);
   // output tile geometry: tw x th = 128 voxels of one frame, tw a power of two minimising padded waste
   int best_tw = 128;

@@ -1,0 +1,129 @@
+// Shared pieces of the tcgen05 GEMM / implicit-GEMM conv kernels: parameters, tile-order mapping and the fused
+// epilogue applied to one chunk of CH accumulator columns held in registers.
+#pragma once
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace dove {
+
+struct GemmParams {
+  int num_m_tiles, num_n_tiles, num_kb;
+  int M;   // dense: valid rows
+  // conv geometry
+  int tw, th, tiles_w, tiles_h;
+  int band_h, To;   // L2-friendly tile order: bands of band_h tile-rows, all To frames of a band before the next
+  int Ho, Wo;
+  int kh, kw, cin_blocks;
+  int stride, pad;
+  // epilogue
+  int epi;
+  bf16* C;
+  long long ldc;
+  const bf16* bias;
+  const bf16* aux;
+  long long ld_aux;
+  const bf16* gate0;
+  const bf16* gate1;
+  int split_row;
+  int n_valid;    // columns stored
+  int out_mode;   // 0 row-major [rows, ldc], 1 planar [n][rows_total]
+  long long rows_total;
+};
+
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+  // 0.5*x*(1+tanh(sqrt(2/pi)*(x+0.044715x^3))), tanh(y) = 1 - 2/(exp(2y)+1)
+  const float kBeta = 0.7978845608028654f, kKappa = 0.044715f;
+  float inner = kBeta * (x + kKappa * x * x * x);
+  float t = 1.0f - __fdividef(2.0f, __expf(2.0f * inner) + 1.0f);
+  return 0.5f * x * (1.0f + t);
+}
+
+// conv m-tile index -> (frame t, tile row hy, tile col wx).  Tiles are ordered band-major: a band is `band_h` tile
+// rows; within a band all frames are visited before moving on, so the 3 output frames that share an input
+// frame (and the 3 tile rows that share an input row) are processed while that input is still in L2.
+__device__ __forceinline__ void conv_tile_coords(const GemmParams& p, int mt, int& t, int& hy, int& wx) {
+  const int full_band = p.band_h * p.tiles_w * p.To;
+  const int b = mt / full_band;
+  const int r = mt - b * full_band;
+  const int gb = min(p.band_h, p.tiles_h - b * p.band_h);
+  const int pb = gb * p.tiles_w;
+  t = r / pb;
+  const int rr = r - t * pb;
+  hy = b * p.band_h + rr / p.tiles_w;
+  wx = rr % p.tiles_w;
+}
+
+// Fused epilogue for CH consecutive accumulator columns (n0 .. n0+CH) of output row `row`.
+template <int CH>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t* v, long long row, int n0,
+                                               const bf16* gate) {
+  float r[CH];
+  if (p.bias) {
+    const uint4* bp = reinterpret_cast<const uint4*>(p.bias + n0);
+#pragma unroll
+    for (int j = 0; j < CH / 8; ++j) {
+      const uint4 b4 = bp[j];
+      const uint32_t bu[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 b2 = unpack_bf16x2(bu[k]);
+        r[j * 8 + 2 * k] = bf16_round(__uint_as_float(v[j * 8 + 2 * k]) + b2.x);
+        r[j * 8 + 2 * k + 1] = bf16_round(__uint_as_float(v[j * 8 + 2 * k + 1]) + b2.y);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < CH; ++i) r[i] = bf16_round(__uint_as_float(v[i]));
+  }
+  if (p.epi == DOVE_EPI_GELU_TANH) {
+#pragma unroll
+    for (int i = 0; i < CH; ++i) r[i] = gelu_tanh_f(r[i]);
+  } else if (p.epi == DOVE_EPI_GATED_RES || p.epi == DOVE_EPI_ADD) {
+    const uint4* ap = reinterpret_cast<const uint4*>(p.aux + row * p.ld_aux + n0);
+    const uint4* gp = reinterpret_cast<const uint4*>((gate ? gate : p.aux) + n0);
+#pragma unroll
+    for (int j = 0; j < CH / 8; ++j) {
+      const uint4 a4 = ap[j];
+      const uint32_t au[4] = {a4.x, a4.y, a4.z, a4.w};
+      uint4 g4 = make_uint4(0, 0, 0, 0);
+      if (p.epi == DOVE_EPI_GATED_RES) g4 = gp[j];
+      const uint32_t gu[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 a2 = unpack_bf16x2(au[k]);
+        const int i = j * 8 + k * 2;
+        if (p.epi == DOVE_EPI_GATED_RES) {
+          const float2 g2 = unpack_bf16x2(gu[k]);
+          r[i] = a2.x + bf16_round(g2.x * r[i]);
+          r[i + 1] = a2.y + bf16_round(g2.y * r[i + 1]);
+        } else {
+          r[i] += a2.x;
+          r[i + 1] += a2.y;
+        }
+      }
+    }
+  }
+  if (p.out_mode == 0 && n0 + CH <= p.n_valid) {
+    uint4* cp = reinterpret_cast<uint4*>(p.C + row * p.ldc + n0);
+#pragma unroll
+    for (int j = 0; j < CH / 8; ++j) {
+      uint4 o;
+      o.x = pack_bf16x2(r[j * 8 + 0], r[j * 8 + 1]);
+      o.y = pack_bf16x2(r[j * 8 + 2], r[j * 8 + 3]);
+      o.z = pack_bf16x2(r[j * 8 + 4], r[j * 8 + 5]);
+      o.w = pack_bf16x2(r[j * 8 + 6], r[j * 8 + 7]);
+      cp[j] = o;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      const int n = n0 + i;
+      if (n < p.n_valid) {
+        if (p.out_mode == 0) p.C[row * p.ldc + n] = __float2bfloat16_rn(r[i]);
+        else p.C[static_cast<long long>(n) * p.rows_total + row] = __float2bfloat16_rn(r[i]);
+      }
+    }
+  }
+}
+
+}  // namespace dove

@@ -46,6 +46,9 @@ int dove_abi_version(void);
 int dove_init(int device);
 const char* dove_last_error(void);
 int dove_num_sms(void);
+/* Tuning / test switches.  "conv2cta": 1 (default) = big stride-1 3x3(x3) convs on images >= 256 wide run on the
+ * CTA-pair kernel (cta_group::2 MMA + in-smem reuse of the W taps), 0 = always the 1-CTA kernel (tests). */
+int dove_set_option(const char* name, int value);
 
 /* ---- DiT -------------------------------------------------------------------------------------------------- */
 

@@ -302,3 +302,28 @@ def test_layout_and_sampling(L):
     L.post_scale(noise, o)
     torch.cuda.synchronize()
     assert torch.equal(o.float(), rb(rb(rb(noise.float() * 0.5) + 0.5).clamp(0, 1)))
+
+
+@pytest.mark.parametrize("variant", [1, 0])
+@pytest.mark.parametrize("cin,cout,T,H,W,kt", [(128, 128, 2, 6, 256, 3), (128, 256, 2, 5, 384, 3), (256, 256, 2, 4, 320, 1),
+                                               (256, 128, 1, 8, 256, 3), (64, 128, 3, 3, 640, 3)])
+def test_conv_cta_pair(L, cin, cout, T, H, W, kt, variant):
+    """Wide stride-1 3x3(x3) convs: CTA-pair kernel (cta_group::2 + W-tap reuse through shifted smem descriptors).
+    variant 1 = CTA-pair kernel (shipping), 0 = 1-CTA kernel on the same problem."""
+    L.set_option("conv2cta", variant)
+    try:
+        x = randn(T + kt - 1, H, W, cin, seed=1)
+        K = kt * 9 * cin
+        w = randn(cout, K, std=K ** -0.5, seed=2)
+        bias = randn(cout, std=0.1, seed=3)
+        aux = randn(T, H, W, cout, seed=7)
+        y = torch.full((T, H, W, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+        L.conv_cl(x, w, bias, y, T, kt, 3, 3, 1, 1, H, W, cout, epilogue=L.EPI_ADD, aux=aux)
+        torch.cuda.synchronize()
+        ref = conv_ref(x, w, bias, kt, 3, 3, 1, 1, cin, cout)
+        e = rel_l2(y, rb(rb(ref) + aux.float()))
+        print(f"conv2cta variant{variant} cin{cin} cout{cout} T{T} {H}x{W} kt{kt}: rel_l2={e:.3e}")
+        assert torch.isfinite(y.float()).all()
+        assert e < TOL
+    finally:
+        L.set_option("conv2cta", 1)
