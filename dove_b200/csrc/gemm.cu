@@ -28,7 +28,11 @@ struct GemmCfg {
   static constexpr size_t SMEM = 1024 + STAGES * (A_BYTES + B_BYTES) + 256;
 };
 
-template <int BN, bool kConv>
+// kTrans (conv only, BN = 256): operand roles are swapped — the M = 128 operand is the WEIGHT tile (128 output
+// channels), the N = 256 operand is the activation box (256 voxels) — so that 128-channel convs still issue N = 256
+// MMAs (an M128 x N128 MMA re-reads 128 B/clk of operands and saturates shared memory at ~42 % tensor pipe).
+// The accumulator is then [channel lane][voxel column] and the epilogue writes it back channels-last.
+template <int BN, bool kConv, bool kTrans = false>
 __global__ void __launch_bounds__(320, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
@@ -90,12 +94,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int dw = tap % p.kw;
           const int dh = (tap / p.kw) % p.kh;
           const int dt = tap / (p.kw * p.kh);
-          tma_load_4d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], c0, w0 * p.stride + dw - p.pad,
-                      h0 * p.stride + dh - p.pad, t + dt);
+          tma_load_4d(kTrans ? sB + stage * Cfg::B_BYTES : sA + stage * Cfg::A_BYTES, &tmA, &full[stage], c0,
+                      w0 * p.stride + dw - p.pad, h0 * p.stride + dh - p.pad, t + dt);
         } else {
           tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], kb * 64, mt * 128);
         }
-        tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * 64, nt * BN);
+        if (kTrans) tma_load_2d(sA + stage * Cfg::A_BYTES, &tmB, &full[stage], kb * 64, nt * 128);
+        else tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * 64, nt * BN);
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
@@ -140,6 +145,53 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int mt = tile / p.num_n_tiles, nt = tile % p.num_n_tiles;
+      if (kTrans) {
+        // lane = output channel, accumulator columns = the tile's 256 voxels (th rows x tw cols, tw a power of 2)
+        int t, hy, wx;
+        conv_tile_coords(p, mt, t, hy, wx);
+        const int ch = nt * 128 + r_in_tile;
+        const float bias_v = p.bias ? __bfloat162float(p.bias[ch]) : 0.f;
+        const int tw_mask = p.tw - 1, tw_shift = 31 - __clz(p.tw);
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+        for (int c0 = half * 32; c0 < BN; c0 += 64) {
+          uint32_t v[32];
+          tmem_ld32(t_row + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            // voxels c0+i (even lanes store it) and c0+i+1 (odd lanes): lane pairs swap one value so that every
+            // lane stores a packed (channel, channel+1) pair -> 64 contiguous bytes per voxel per half-warp
+            const int vi = c0 + i + (lane & 1);
+            const int h = hy * p.th + (vi >> tw_shift), w = wx * p.tw + (vi & tw_mask);
+            const bool ok = (h < p.Ho) && (w < p.Wo);
+            const long long row = (static_cast<long long>(t) * p.Ho + h) * p.Wo + w;
+            float a = bf16_round(__uint_as_float(v[i]) + bias_v);
+            float b = bf16_round(__uint_as_float(v[i + 1]) + bias_v);
+            const float send = (lane & 1) ? a : b;
+            const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+            float lo = (lane & 1) ? recv : a;     // channel (ch & ~1)
+            float hi = (lane & 1) ? b : recv;     // channel (ch | 1)
+            if (ok) {
+              const long long off = row * p.ldc + (ch & ~1);
+              if (p.epi == DOVE_EPI_ADD) {
+                const float2 x2 = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p.aux + row * p.ld_aux + (ch & ~1)));
+                lo += x2.x;
+                hi += x2.y;
+              }
+              *reinterpret_cast<uint32_t*>(p.C + off) = pack_bf16x2(lo, hi);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+        continue;
+      }
       long long row;
       bool valid;
       if (kConv) {
@@ -196,6 +248,22 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   const int grid = total < num_sms() ? total : num_sms();
   umma_gemm_kernel<BN, kConv><<<grid, 320, Cfg::SMEM, st>>>(tmA, tmB, p);
   DOVE_LAUNCH_CHECK("umma_gemm_kernel");
+  return DOVE_OK;
+}
+
+static int launch_conv_trans(const CUtensorMap& tmX, const CUtensorMap& tmW, const GemmParams& p, cudaStream_t st) {
+  using Cfg = GemmCfg<256>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(umma_gemm_kernel<256, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(Cfg::SMEM));
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(umma_gemm_kernel trans)");
+    attr_set = true;
+  }
+  const int total = p.num_m_tiles * p.num_n_tiles;
+  const int grid = total < num_sms() ? total : num_sms();
+  umma_gemm_kernel<256, true, true><<<grid, 320, Cfg::SMEM, st>>>(tmX, tmW, p);
+  DOVE_LAUNCH_CHECK("umma_gemm_kernel<trans>");
   return DOVE_OK;
 }
 
@@ -289,7 +357,7 @@ extern "C" int dove_conv_cl_bf16(const void* x, const void* w, const void* bias,
   {   // CTA-pair kernel with in-smem reuse of the W taps for the big stride-1 3x3(x3) convs on wide images
     const int opt = get_option_conv2cta();
     if (opt != 0 && stride == 1 && kh == 3 && kw == 3 && pad == 1 && out_mode == 0 && Wo >= 256 && Hin == Ho &&
-        Win == Wo && (Cout_pad == 128 || Cout_pad % 256 == 0) && cout_valid == Cout_pad) {
+        Win == Wo && Cout_pad % 256 == 0 && cout_valid == Cout_pad) {
       GemmParams q{};
       q.Ho = Ho;
       q.Wo = Wo;
@@ -308,6 +376,72 @@ extern "C" int dove_conv_cl_bf16(const void* x, const void* w, const void* bias,
       q.rows_total = static_cast<long long>(Tout) * Ho * Wo;
       return conv2cta_dispatch(x, w, Tout, Hin, Win, Cin, Cout_pad, kt, Ho, Wo, q, static_cast<cudaStream_t>(stream));
     }
+  }
+  // 128-channel-out convs on large images: swapped operand roles (weights = M 128, voxels = N 256)
+  const bool trans = get_option_conv2cta() != 0 && stride == 1 && out_mode == 0 && Cout_pad == 128 &&
+                     cout_valid == 128 && static_cast<long long>(Ho) * Wo >= 4096;
+  if (trans) {
+    int best_tw = 256;
+    long long best_cost = -1;
+    for (int tw = 256; tw >= 8; tw >>= 1) {
+      const int th = 256 / tw;
+      const long long cost = static_cast<long long>((Wo + tw - 1) / tw) * ((Ho + th - 1) / th);
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost;
+        best_tw = tw;
+      }
+    }
+    const int tw = best_tw, th = 256 / tw;
+    const int Tin = Tout + kt - 1;
+    CUtensorMap tmX, tmW;
+    {
+      uint64_t dims[4] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(Win), static_cast<uint64_t>(Hin),
+                          static_cast<uint64_t>(Tin)};
+      uint64_t strides[3] = {static_cast<uint64_t>(Cin) * 2, static_cast<uint64_t>(Win) * Cin * 2,
+                             static_cast<uint64_t>(Hin) * Win * Cin * 2};
+      uint32_t box[4] = {64, static_cast<uint32_t>(tw), static_cast<uint32_t>(th), 1};
+      if (int e = make_tmap_bf16(&tmX, x, 4, dims, strides, box, nullptr)) return e;
+    }
+    const int Ktot = kt * kh * kw * Cin;
+    {
+      uint64_t dims[2] = {static_cast<uint64_t>(Ktot), static_cast<uint64_t>(Cout_pad)};
+      uint64_t strides[1] = {static_cast<uint64_t>(Ktot) * 2};
+      uint32_t box[2] = {64, 128};
+      if (int e = make_tmap_bf16(&tmW, w, 2, dims, strides, box, nullptr)) return e;
+    }
+    GemmParams q{};
+    q.tw = tw;
+    q.th = th;
+    q.tiles_w = (Wo + tw - 1) / tw;
+    q.tiles_h = (Ho + th - 1) / th;
+    q.num_m_tiles = Tout * q.tiles_w * q.tiles_h;
+    q.num_n_tiles = Cout_pad / 128;
+    q.num_kb = Ktot / 64;
+    q.To = Tout;
+    {
+      const double row_bytes = static_cast<double>(Win) * Cin * 2.0 * Tin * th;
+      int bh = static_cast<int>(32.0e6 / row_bytes);
+      if (bh < 1) bh = 1;
+      if (bh > q.tiles_h) bh = q.tiles_h;
+      q.band_h = bh;
+    }
+    q.Ho = Ho;
+    q.Wo = Wo;
+    q.kh = kh;
+    q.kw = kw;
+    q.cin_blocks = Cin / 64;
+    q.stride = 1;
+    q.pad = pad;
+    q.epi = epilogue;
+    q.C = static_cast<bf16*>(y);
+    q.ldc = ldy;
+    q.bias = static_cast<const bf16*>(bias);
+    q.aux = static_cast<const bf16*>(aux);
+    q.ld_aux = ld_aux;
+    q.n_valid = cout_valid;
+    q.out_mode = 0;
+    q.rows_total = static_cast<long long>(Tout) * Ho * Wo;
+    return launch_conv_trans(tmX, tmW, q, static_cast<cudaStream_t>(stream));
   }
   const int bn = pick_bn(Cout_pad);
   // output tile geometry: tw x th = 128 voxels of one frame, tw a power of two minimising padded waste

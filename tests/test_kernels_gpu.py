@@ -306,7 +306,10 @@ def test_layout_and_sampling(L):
 
 @pytest.mark.parametrize("variant", [1, 0])
 @pytest.mark.parametrize("cin,cout,T,H,W,kt", [(128, 128, 2, 6, 256, 3), (128, 256, 2, 5, 384, 3), (256, 256, 2, 4, 320, 1),
-                                               (256, 128, 1, 8, 256, 3), (64, 128, 3, 3, 640, 3)])
+                                               (256, 128, 1, 8, 256, 3), (64, 128, 3, 3, 640, 3),
+                                               # Cout = 128 on >= 4096-voxel frames: swapped-operand kernel (N = 256 voxels)
+                                               (128, 128, 2, 16, 256, 3), (256, 128, 1, 24, 200, 3), (64, 128, 2, 64, 64, 1),
+                                               (128, 128, 3, 33, 136, 3)])
 def test_conv_cta_pair(L, cin, cout, T, H, W, kt, variant):
     """Wide stride-1 3x3(x3) convs: CTA-pair kernel (cta_group::2 + W-tap reuse through shifted smem descriptors).
     variant 1 = CTA-pair kernel (shipping), 0 = 1-CTA kernel on the same problem."""
