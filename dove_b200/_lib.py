@@ -57,6 +57,9 @@ _SIGS = {
     "dove_cl_to_ncthw_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "dove_gaussian_sample_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_void_p]),
     "dove_post_scale_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "dove_upscale_normalize_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "dove_blend_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int,
+                                c_int64, c_int64, c_int64, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS)
@@ -264,3 +267,39 @@ def gaussian_sample(moments, noise, z, nvox, scaling):
 def post_scale(x, y):
     _call("dove_post_scale_bf16", _p(_bf16c(x)), _p(y), x.numel(), _stream())
     return y
+
+
+def blend(a, b, axis, extent, layout):
+    """In-place linear blend of tile `b` with its neighbour `a` along `axis` ("v" rows / "h" cols).
+    layout "cl": tensors [T, Y, X, C];  layout "planar": tensors [C, T, Y, X]."""
+    if layout == "cl":
+        T, Ya, Xa, C = a.shape
+        _, Yb, Xb, _ = b.shape
+        outer, inner = T, C
+        a_s = (a.stride(0), a.stride(1), a.stride(2))
+        b_s = (b.stride(0), b.stride(1), b.stride(2))
+    else:
+        Cc, T, Ya, Xa = a.shape
+        _, _, Yb, Xb = b.shape
+        assert a.stride(1) == Ya * Xa and a.stride(0) == T * Ya * Xa and b.stride(1) == Yb * Xb
+        outer, inner = Cc * T, 1
+        a_s = (Ya * Xa, a.stride(2), a.stride(3))
+        b_s = (Yb * Xb, b.stride(2), b.stride(3))
+    if axis == "v":
+        e = min(Ya, Yb, extent)
+        assert Xa == Xb
+        args = (outer, e, Xb, inner, a_s[0], a_s[1], a_s[2], Ya, b_s[0], b_s[1], b_s[2])
+    else:
+        e = min(Xa, Xb, extent)
+        assert Ya == Yb
+        args = (outer, e, Yb, inner, a_s[0], a_s[2], a_s[1], Xa, b_s[0], b_s[2], b_s[1])
+    if e > 0:
+        _call("dove_blend_bf16", _p(a), _p(b), *args, _stream())
+    return b
+
+
+def upscale_normalize(lr, out, scale):
+    F, C, h, w = lr.shape
+    assert C == 3 and lr.dtype == torch.float32 and lr.is_contiguous() and out.dtype == torch.float32
+    _call("dove_upscale_normalize_f32", _p(lr), _p(out), F, h, w, scale, _stream())
+    return out

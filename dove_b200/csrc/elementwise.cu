@@ -384,6 +384,58 @@ __global__ void upsample_nearest_kernel(const bf16* __restrict__ x, bf16* __rest
   }
 }
 
+// ------------------------------------------------------------------------------------------------ pre-processing
+// lr [F, 3, h, w] fp32 (0..255) -> out [3, F, S*h, S*w] fp32 = bilinear(align_corners=False) upscale, then /255*2-1
+// (ref: inference_script.py:672-679, F.interpolate(scale_factor=upscale, mode="bilinear") on the 0-255 floats)
+__global__ void upscale_normalize_kernel(const float* __restrict__ lr, float* __restrict__ out, int F, int h, int w,
+                                         int S) {
+  const int H = h * S, W = w * S;
+  const long long total = static_cast<long long>(3) * F * H * W;
+  const float rs = 1.0f / static_cast<float>(S);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % W);
+    const int y = static_cast<int>((i / W) % H);
+    const int f = static_cast<int>((i / (static_cast<long long>(W) * H)) % F);
+    const int c = static_cast<int>(i / (static_cast<long long>(W) * H * F));
+    float sy = rs * (y + 0.5f) - 0.5f, sx = rs * (x + 0.5f) - 0.5f;
+    sy = sy < 0.f ? 0.f : sy;
+    sx = sx < 0.f ? 0.f : sx;
+    const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
+    const int y1 = y0 + (y0 < h - 1), x1 = x0 + (x0 < w - 1);
+    const float ly = sy - y0, lx = sx - x0, hy = 1.f - ly, hx = 1.f - lx;
+    const float* src = lr + (static_cast<long long>(f) * 3 + c) * h * w;
+    const float v = hy * (hx * src[y0 * w + x0] + lx * src[y0 * w + x1]) +
+                    ly * (hx * src[y1 * w + x0] + lx * src[y1 * w + x1]);
+    out[i] = v / 255.0f * 2.0f - 1.0f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ tile blend
+// b[o, p, q, c] = bf16(bf16(a[o, P_a - e + p, q, c]*(1 - p/e)) + bf16(b[o, p, q, c]*(p/e)))  for p < e  (in place)
+// generic strides: (outer, blended axis, other axis, inner) — serves blend_v and blend_h on channels-last latents and
+// on planar pixel tiles.
+__global__ void blend_kernel(const bf16* __restrict__ a, bf16* __restrict__ b, int outer, int e, int other,
+                             int inner, long long a_so, long long a_sp, long long a_sq, int a_len,
+                             long long b_so, long long b_sp, long long b_sq) {
+  const long long total = static_cast<long long>(outer) * e * other * inner;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % inner);
+    long long r = i / inner;
+    const int q = static_cast<int>(r % other);
+    r /= other;
+    const int pp = static_cast<int>(r % e);
+    const int o = static_cast<int>(r / e);
+    const float wb = static_cast<float>(static_cast<double>(pp) / e);
+    const float wa = static_cast<float>(1.0 - static_cast<double>(pp) / e);
+    const float av = __bfloat162float(a[o * a_so + (a_len - e + pp) * a_sp + q * a_sq + c]);
+    bf16* bp = b + o * b_so + pp * b_sp + q * b_sq + c;
+    const float bv = __bfloat162float(*bp);
+    *bp = __float2bfloat16_rn(bf16_round(av * wa) + bf16_round(bv * wb));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ layout glue
 template <typename TIn>
 __global__ void pixels_to_cl_kernel(const TIn* __restrict__ x, bf16* __restrict__ y, long long nvox, int Cpad) {
@@ -663,6 +715,28 @@ extern "C" int dove_gaussian_sample_bf16(const void* moments, const void* noise,
   gaussian_sample_kernel<<<grid_for(nvox * 16, 256), 256, 0, ST(stream)>>>(
       static_cast<const bf16*>(moments), static_cast<const bf16*>(noise), static_cast<bf16*>(z), nvox, scaling);
   DOVE_LAUNCH_CHECK("gaussian_sample_kernel");
+  return DOVE_OK;
+}
+
+extern "C" int dove_upscale_normalize_f32(const float* lr, float* out, int F, int h, int w, int scale, void* stream) {
+  if (int e = ensure_init()) return e;
+  DOVE_CHECK_ARG(F > 0 && h > 0 && w > 0 && scale >= 1, "upscale: bad shape");
+  const long long total = static_cast<long long>(3) * F * h * scale * w * scale;
+  upscale_normalize_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(lr, out, F, h, w, scale);
+  DOVE_LAUNCH_CHECK("upscale_normalize_kernel");
+  return DOVE_OK;
+}
+
+extern "C" int dove_blend_bf16(const void* a, void* b, int outer, int extent, int other, int inner, int64_t a_so,
+                               int64_t a_sp, int64_t a_sq, int a_len, int64_t b_so, int64_t b_sp, int64_t b_sq,
+                               void* stream) {
+  if (int e = ensure_init()) return e;
+  DOVE_CHECK_ARG(outer > 0 && extent > 0 && other > 0 && inner > 0 && a_len >= extent, "blend: bad shape");
+  const long long total = static_cast<long long>(outer) * extent * other * inner;
+  blend_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(static_cast<const bf16*>(a), static_cast<bf16*>(b), outer,
+                                                             extent, other, inner, a_so, a_sp, a_sq, a_len, b_so, b_sp,
+                                                             b_sq);
+  DOVE_LAUNCH_CHECK("blend_kernel");
   return DOVE_OK;
 }
 

@@ -121,3 +121,35 @@ def make_process_fn(pipe, empty_prompt_embedding, sr_noise_step=399, noise_step=
         return pipe.one_step_sr(unit, empty_prompt_embedding, sr_noise_step=sr_noise_step, noise=noise,
                                 noise_step=noise_step)
     return fn
+
+
+def preprocess_frames(frames_u8, upscale=4, device="cuda"):
+    """GPU version of ref inference_script.py:192-235 + :670-679 (decode excluded): frames [F,H,W,3] uint8 ->
+    ([1,3,F',4H',4W'] fp32 in [-1,1] on the device, pad_f, pad_h, pad_w).  Frames are padded to 8k+1 by repeating the
+    last frame, H/W to multiples of 16 with zeros (bottom/right), then bilinear x`upscale` on the 0..255 floats and
+    x/255*2-1 run in one kernel.  Only the small low-resolution clip crosses PCIe."""
+    from . import _lib as L
+    from .bookkeeping import frame_padding, spatial_padding
+    F, H, W, C = frames_u8.shape
+    pad_f, pad_h, pad_w = frame_padding(F), spatial_padding(H), spatial_padding(W)
+    x = frames_u8.to(device, non_blocking=True)
+    if pad_f:
+        x = torch.cat([x, x[-1:].repeat(pad_f, 1, 1, 1)], dim=0)
+    if pad_h or pad_w:
+        x = torch.nn.functional.pad(x, (0, 0, 0, pad_w, 0, pad_h))
+    lr = x.permute(0, 3, 1, 2).float().contiguous()                       # [F,3,h,w] 0..255
+    Fp, _, h, w = lr.shape
+    out = torch.empty(1, 3, Fp, h * upscale, w * upscale, dtype=torch.float32, device=lr.device)
+    L.upscale_normalize(lr, out[0], upscale)
+    return out, pad_f, pad_h, pad_w
+
+
+def remove_padding_and_extra_frames(video, pad_f, pad_h, pad_w, upscale=4):
+    """ref inference_script.py:238-246 (called with pad*4 at :731)."""
+    if pad_f > 0:
+        video = video[:, :, :-pad_f]
+    if pad_h > 0:
+        video = video[:, :, :, :-pad_h * upscale]
+    if pad_w > 0:
+        video = video[:, :, :, :, :-pad_w * upscale]
+    return video

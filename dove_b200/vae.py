@@ -218,7 +218,7 @@ class AutoencoderKLCogVideoX:
         T = t1 - t0
         xin = self._empty(T + 2, H, W, 64)
         # per-channel planes of this frame batch are strided inside pix: gather through a contiguous view
-        src = pix[:, t0:t1].contiguous() if (t0 != 0 or t1 != F) else pix
+        src = pix[:, t0:t1].contiguous()
         L.pixels_to_cl(src, xin[2:], T, H, W, 64)
         x = self._causal_conv(self.enc_conv_in, xin, T, H, W, cache, "conv_in")
         del xin
@@ -259,27 +259,79 @@ class AutoencoderKLCogVideoX:
             total += t
         return total
 
-    def _check_tiling(self, h, w, min_h, min_w):
-        if self.use_tiling and (w > min_w or h > min_h):
-            raise NotImplementedError(
-                "VAE spatial tiling (--is_vae_st / enable_tiling) is the 'next' row f-2 of SURVEY.md section 8 and "
-                "is not implemented yet; 180 GB of HBM fits the untiled pass, run without enable_tiling()")
+    def tile_ints(self):
+        """Integers of diffusers' tiled_encode / tiled_decode (pinned: 200/288, 5/9, 25/36 | 25/36, 40/72, 200/288)."""
+        c = self.config
+        sf = 2 ** (len(c.block_out_channels) - 1)
+        smin_h, smin_w = c.sample_height // 2, c.sample_width // 2
+        lmin_h, lmin_w = int(smin_h / sf), int(smin_w / sf)
+        oh, ow = 1 / 6, 1 / 5
+        enc = dict(tile_h=smin_h, tile_w=smin_w, stride_h=int(smin_h * (1 - oh)), stride_w=int(smin_w * (1 - ow)),
+                   blend_h=int(lmin_h * oh), blend_w=int(lmin_w * ow))
+        enc["limit_h"], enc["limit_w"] = lmin_h - enc["blend_h"], lmin_w - enc["blend_w"]
+        dec = dict(tile_h=lmin_h, tile_w=lmin_w, stride_h=int(lmin_h * (1 - oh)), stride_w=int(lmin_w * (1 - ow)),
+                   blend_h=int(smin_h * oh), blend_w=int(smin_w * ow))
+        dec["limit_h"], dec["limit_w"] = smin_h - dec["blend_h"], smin_w - dec["blend_w"]
+        return enc, dec
+
+    def _encode_untiled(self, pix):
+        """pix [3,F,H,W] contiguous -> moments channels-last [T',H/8,W/8,32] (frame-batched, fresh conv cache)."""
+        _, F, H, W = pix.shape
+        cache, outs = {}, []
+        for (s, e) in self.frame_batches(F, self.num_sample_frames_batch_size):
+            m, _ = self._encoder_batch(pix, s, e, F, H, W, cache)
+            outs.append(m)
+        return torch.cat(outs, dim=0) if len(outs) > 1 else outs[0]
+
+    def _blend_and_stitch(self, rows, ti, layout, out):
+        """diffusers blend_v / blend_h in raster order, in place on the un-cropped tiles, then crop + place."""
+        yo = 0
+        for i, row in enumerate(rows):
+            xo = 0
+            for j, tile in enumerate(row):
+                if i > 0:
+                    L.blend(rows[i - 1][j], tile, "v", ti["blend_h"], layout)
+                if j > 0:
+                    L.blend(row[j - 1], tile, "h", ti["blend_w"], layout)
+                if layout == "cl":
+                    crop = tile[:, :ti["limit_h"], :ti["limit_w"]]
+                    out[:, yo:yo + crop.shape[1], xo:xo + crop.shape[2]] = crop
+                    dy, dx = crop.shape[1], crop.shape[2]
+                else:
+                    crop = tile[:, :, :ti["limit_h"], :ti["limit_w"]]
+                    out[:, :, yo:yo + crop.shape[2], xo:xo + crop.shape[3]] = crop
+                    dy, dx = crop.shape[2], crop.shape[3]
+                xo += dx
+            yo += dy
+        return out
+
+    def _encode_tiled(self, pix):
+        """AutoencoderKLCogVideoX.tiled_encode (`--is_vae_st`): 240x360 px tiles at stride 200x288, each with its own
+        frame-batched pass (so GroupNorm statistics are per tile), linear blend of 5/9 latent px, crop 25x36."""
+        enc, _ = self.tile_ints()
+        _, F, H, W = pix.shape
+        rows = []
+        for i in range(0, H, enc["stride_h"]):
+            row = []
+            for j in range(0, W, enc["stride_w"]):
+                row.append(self._encode_untiled(pix[:, :, i:i + enc["tile_h"], j:j + enc["tile_w"]].contiguous()))
+            rows.append(row)
+        Tl = rows[0][0].shape[0]
+        out = self._empty(Tl, H // 8, W // 8, 32)
+        return self._blend_and_stitch(rows, enc, "cl", out)
 
     def encode_cl(self, x):
         """x: [1,3,F,H,W] on device (fp32 or bf16) -> (moments channels-last [T',h,w,32], (T',h,w))."""
         assert x.dim() == 5 and x.shape[0] == 1 and x.shape[1] == 3, "batch 1, 3 channels"
         _, _, F, H, W = x.shape
         assert H % 8 == 0 and W % 8 == 0, "H, W must be multiples of 8"
-        self._check_tiling(H, W, self.config.sample_height // 2, self.config.sample_width // 2)
         pix = x[0].contiguous()
-        cache = {}
-        outs, shape = [], None
-        for (s, e) in self.frame_batches(F, self.num_sample_frames_batch_size):
-            m, shp = self._encoder_batch(pix, s, e, F, H, W, cache)
-            outs.append(m)
-            shape = shp
-        mom = torch.cat(outs, dim=0) if len(outs) > 1 else outs[0]
-        return mom, (mom.shape[0], shape[1], shape[2])
+        enc, _ = self.tile_ints()
+        if self.use_tiling and (W > enc["tile_w"] or H > enc["tile_h"]):
+            mom = self._encode_tiled(pix)
+        else:
+            mom = self._encode_untiled(pix)
+        return mom, (mom.shape[0], mom.shape[1], mom.shape[2])
 
     def encode(self, x):
         x = x.to(self._device)
@@ -323,26 +375,49 @@ class AutoencoderKLCogVideoX:
                           out=out.view(3, -1)[:, f_off * H * W:], out_mode=1, plane_stride=F_out * H * W)
         return T
 
-    def decode_scaled(self, z, scale=1.0):
-        """z: [1,16,Tz,h,w] bf16 -> [1,3,F,8h,8w] bf16; `scale` is applied to z first (decode_latents' 1/0.7)."""
-        assert z.dim() == 5 and z.shape[0] == 1 and z.shape[1] == 16
-        _, _, Tz, h, w = z.shape
+    def _decode_untiled(self, zc, scale):
+        """zc [16,Tz,h,w] bf16 contiguous -> [1,3,F,8h,8w] bf16 (frame-batched, fresh conv cache)."""
+        _, Tz, h, w = zc.shape
         sf = 2 ** (len(self.config.block_out_channels) - 1)
-        self._check_tiling(h, w, self.config.sample_height // 2 // sf, self.config.sample_width // 2 // sf)
         batches = self.frame_batches(Tz, self.num_latent_frames_batch_size)
         F_out = 0
-        for bi, (s, e) in enumerate(batches):     # frames produced: first batch keeps frame 0 single
+        for (s, e) in batches:     # frames produced: the first batch keeps frame 0 single
             T = e - s
             for _ in range(2):
                 T = (1 + 2 * (T - 1) if T % 2 else 2 * T) if T > 1 else T
             F_out += T
         out = self._empty(1, 3, F_out, h * sf, w * sf)
-        zc = z[0].to(BF).contiguous()
         cache = {}
         f_off = 0
         for (s, e) in batches:
             f_off += self._decoder_batch(zc, s, e, h, w, scale, cache, out[0], f_off, F_out)
         return out
+
+    def _decode_tiled(self, zc, scale):
+        """AutoencoderKLCogVideoX.tiled_decode: 30x45 latent tiles at stride 25x36, blend 40/72 px, crop 200x288."""
+        _, dec = self.tile_ints()
+        _, Tz, h, w = zc.shape
+        sf = 2 ** (len(self.config.block_out_channels) - 1)
+        rows = []
+        for i in range(0, h, dec["stride_h"]):
+            row = []
+            for j in range(0, w, dec["stride_w"]):
+                tile = zc[:, :, i:i + dec["tile_h"], j:j + dec["tile_w"]].contiguous()
+                row.append(self._decode_untiled(tile, scale)[0])
+            rows.append(row)
+        F_out = rows[0][0].shape[1]
+        out = self._empty(3, F_out, h * sf, w * sf)
+        return self._blend_and_stitch(rows, dec, "planar", out)[None]
+
+    def decode_scaled(self, z, scale=1.0):
+        """z: [1,16,Tz,h,w] bf16 -> [1,3,F,8h,8w] bf16; `scale` is applied to z first (decode_latents' 1/0.7)."""
+        assert z.dim() == 5 and z.shape[0] == 1 and z.shape[1] == 16
+        _, _, Tz, h, w = z.shape
+        zc = z[0].to(BF).contiguous()
+        _, dec = self.tile_ints()
+        if self.use_tiling and (w > dec["tile_w"] or h > dec["tile_h"]):
+            return self._decode_tiled(zc, scale)
+        return self._decode_untiled(zc, scale)
 
     def decode(self, z):
         return SimpleNamespace(sample=self.decode_scaled(z.to(self._device), 1.0))

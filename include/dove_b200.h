@@ -159,6 +159,17 @@ int dove_cl_to_ncthw_bf16(const void* x, void* y, int C, int T, int H, int W, in
 int dove_gaussian_sample_bf16(const void* moments, const void* noise, void* z, int64_t nvox, float scaling,
                               void* stream);
 
+/* Pre-processing of the low-quality clip on the GPU (ref: inference_script.py:672-679): lr [F,3,h,w] fp32 in 0..255
+ * -> out [3, F, scale*h, scale*w] fp32 = bilinear (align_corners=False) upscale, then x/255*2-1. */
+int dove_upscale_normalize_f32(const float* lr, float* out, int F, int h, int w, int scale, void* stream);
+
+/* Linear-ramp blend of two overlapping VAE tiles, in place on b (AutoencoderKLCogVideoX.blend_v / blend_h used by
+ * tiled_encode / tiled_decode, i.e. `--is_vae_st`):  for p < extent:
+ *   b[o,p,q,c] = bf16(bf16(a[o, a_len-extent+p, q, c]*(1-p/extent)) + bf16(b[o,p,q,c]*(p/extent)))
+ * with element strides (so, sp, sq) of the outer / blended / other axes and a contiguous inner axis. */
+int dove_blend_bf16(const void* a, void* b, int outer, int extent, int other, int inner, int64_t a_so, int64_t a_sp,
+                    int64_t a_sq, int a_len, int64_t b_so, int64_t b_sp, int64_t b_sq, void* stream);
+
 /* y = clamp(x*0.5+0.5, 0, 1) elementwise bf16 (ref: inference_script.py:501). */
 int dove_post_scale_bf16(const void* x, void* y, int64_t n, void* stream);
 

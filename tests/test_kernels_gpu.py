@@ -330,3 +330,18 @@ def test_conv_cta_pair(L, cin, cout, T, H, W, kt, variant):
         assert e < TOL
     finally:
         L.set_option("conv2cta", 1)
+
+
+def test_preprocess_matches_reference_recipe(L):
+    """ref inference_script.py:192-235 + :670-679: pad F to 8k+1 / HW to x16, bilinear x4 on 0..255 floats, x/255*2-1."""
+    from dove_b200.runner import preprocess_frames, remove_padding_and_extra_frames
+    g = torch.Generator().manual_seed(0)
+    frames = torch.randint(0, 256, (10, 45, 70, 3), generator=g, dtype=torch.uint8)
+    out, pf, ph, pw = preprocess_frames(frames, 4, "cuda")
+    assert (pf, ph, pw) == (7, 3, 10) and out.shape == (1, 3, 17, 192, 320)
+    x = torch.cat([frames, frames[-1:].repeat(7, 1, 1, 1)], 0)
+    x = F.pad(x, (0, 0, 0, 10, 0, 3)).float().permute(0, 3, 1, 2)
+    ref = (F.interpolate(x, scale_factor=4, mode="bilinear") / 255.0 * 2.0 - 1.0).permute(1, 0, 2, 3)[None]
+    torch.cuda.synchronize()
+    assert (out.cpu() - ref).abs().max().item() < 2e-6
+    assert remove_padding_and_extra_frames(out, pf, ph, pw).shape == (1, 3, 10, 180, 280)

@@ -61,6 +61,40 @@ def test_vae_decode(env, T, h, w):
     gate(f"vae.decode T{T} {h}x{w}", ours, r32, r16)
 
 
+def test_vae_tiled_paths(env):
+    """`--is_vae_st` (enable_tiling): 240x360 px / 30x45 latent tiles, per-tile GroupNorm statistics, linear blends."""
+    m = env["models"]
+    from dove_b200.vae import AutoencoderKLCogVideoX
+    vae = AutoencoderKLCogVideoX(env["vsd"], None, "cuda")
+    vae.enable_tiling()
+    o32, o16 = m.oracle_vae(env["vsd"], "cuda", torch.float32), m.oracle_vae(env["vsd"], "cuda", torch.bfloat16)
+    o32.enable_tiling()
+    o16.enable_tiling()
+    torch.manual_seed(3)
+    x = torch.rand(1, 3, 9, 256, 384, device="cuda") * 2 - 1
+    with torch.no_grad():
+        r32 = o32.encode(x.bfloat16().float()).latent_dist.parameters
+        r16 = o16.encode(x.bfloat16()).latent_dist.parameters
+    ours = vae.encode(x).latent_dist.parameters
+    torch.cuda.synchronize()
+    assert ours.shape == r32.shape == (1, 32, 3, 32, 48)
+    gate("vae.tiled_encode 9x256x384", ours, r32, r16)
+    z = torch.randn(1, 16, 3, 32, 48, device="cuda").bfloat16()
+    with torch.no_grad():
+        d32 = o32.decode(z.float()).sample
+        d16 = o16.decode(z).sample
+    ours = vae.decode(z).sample
+    torch.cuda.synchronize()
+    assert ours.shape == d32.shape == (1, 3, 9, 256, 384)
+    gate("vae.tiled_decode 3x32x48", ours, d32, d16)
+    # below the tile size the tiled switch must not change anything
+    xs = torch.rand(1, 3, 9, 32, 48, device="cuda") * 2 - 1
+    a = vae.encode(xs).latent_dist.parameters
+    vae.use_tiling = False
+    b = vae.encode(xs).latent_dist.parameters
+    assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize("cfgname,F,h,w", [("SMALL_DIT", 2, 8, 12), ("SMALL_DIT", 4, 16, 16), ("WIDE_DIT", 2, 8, 8)])
 def test_dit(env, cfgname, F, h, w):
     m = env["models"]
