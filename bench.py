@@ -111,25 +111,26 @@ def peaks():
 
 
 class ConvTimer:
-    """CUDA-event timing of every implicit-GEMM conv launch (the dominant kernel) inside the timed region."""
+    """CUDA-event timing of every implicit-GEMM conv launch (the dominant kernel family) inside the timed region,
+    grouped by problem class (Cin, Cout, kt, T, H, W)."""
 
     def __init__(self, L):
-        self.L, self.ev, self.flops, self.orig = L, [], 0.0, L.conv_cl
+        self.L, self.ev, self.orig = L, [], L.conv_cl
 
     def __enter__(self):
-        L = self.L
-
         def timed(x, w, bias, y, Tout, kt, kh, kw, stride, pad, Ho, Wo, cout_valid, **kw_):
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
             r = self.orig(x, w, bias, y, Tout, kt, kh, kw, stride, pad, Ho, Wo, cout_valid, **kw_)
             e.record()
-            self.ev.append((s, e))
             cin_real = self.cin_real.get(id(w), x.shape[-1])
-            self.flops += 2.0 * kt * kh * kw * cin_real * cout_valid * Tout * Ho * Wo
+            flops = 2.0 * kt * kh * kw * cin_real * cout_valid * Tout * Ho * Wo
+            nbytes = 2.0 * (x.shape[-1] * (Tout + kt - 1) * x.shape[1] * x.shape[2] + cout_valid * Tout * Ho * Wo) \
+                + 2.0 * kt * kh * kw * x.shape[-1] * cout_valid
+            self.ev.append((s, e, flops, nbytes, (cin_real, cout_valid, kt, Tout, Ho, Wo, stride)))
             return r
         self.cin_real = {}
-        L.conv_cl = timed
+        self.L.conv_cl = timed
         return self
 
     def register_real_cin(self, vae):
@@ -141,8 +142,19 @@ class ConvTimer:
 
     def result(self):
         torch.cuda.synchronize()
-        ms = sum(s.elapsed_time(e) for s, e in self.ev)
-        return self.flops, ms, len(self.ev)
+        tot_f = tot_ms = 0.0
+        classes = {}
+        for s, e, f, b, key in self.ev:
+            ms = s.elapsed_time(e)
+            tot_f += f
+            tot_ms += ms
+            c = classes.setdefault(key, [0, 0.0, 0.0, 0.0])
+            c[0] += 1
+            c[1] += ms
+            c[2] += f
+            c[3] += b
+        top = max(classes.items(), key=lambda kv: kv[1][1]) if classes else None
+        return tot_f, tot_ms, len(self.ev), top
 
 
 def _all_convs(vae):
@@ -215,16 +227,39 @@ def cpu_reference_sample(seconds_budget, layers, steps=1, warmup=0, weights_from
 def run_reference(args, rank):
     if rank != 0:
         return
-    cb, sec = cpu_reference_sample(1e9, args.layers, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    # bounded: at most --steps timed runs, stop early once ~90 s of timed CPU work has accumulated
+    cb, sec = cpu_reference_sample(90.0, args.layers, steps=max(1, args.steps), warmup=min(args.warmup, 1))
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "cfg-2 33x768x1280 one-step VSR; CPU arm timed on a 9x96x160 crop (bounded sample)",
+            "config": {"workload": "cfg-2 33x768x1280 one-step VSR; CPU arm timed on a 9x32x48 crop (bounded sample)",
                        "layers": args.layers},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def roofline(pk, conv_flops, conv_ms, conv_launches, top, ms_total, steps):
+    """Dominant kernel = the conv launch class with the largest summed time in the step (the 128->128 3x3x3 causal
+    convs at full resolution).  achieved = algorithmic FLOPs of ONE such launch / its mean CUDA-event duration.
+    `traffic`: dram read+write bytes of the same launch from the committed ncu --set full capture
+    (profiles/r01_ncu_conv_trans128.txt), next to the algorithmic bytes (activations in+out once, weights once)."""
+    (cin, cout, kt, T, Ho, Wo, stride), (n, ms, fl, by) = top
+    ach = fl / (ms / 1e3) / 1e12
+    fam = conv_flops / (conv_ms / 1e3) / 1e12
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (2 launches captured: 4.98 / 7.49 GB)
+    NCU_TRAFFIC = {(128, 128, 3, 8, 768, 1280): 4.98e9}
+    return {"bound": "tensor",
+            "kernel": f"tcgen05 implicit-GEMM conv, class Cin{cin} Cout{cout} kt{kt} T{T} {Ho}x{Wo}"
+                      + (" [umma_gemm_kernel<256,conv,trans>]" if cout == 128 else " [conv2cta_kernel<256>]"),
+            "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
+            "traffic": NCU_TRAFFIC.get((cin, cout, kt, T, Ho, Wo)), "algorithmic_bytes": by / n,
+            "flops_per_launch": fl / n, "ms_per_launch": ms / n, "launches_per_step": n / steps,
+            "peak_source": pk["source"] + " (sustained cuBLAS bf16; burst " + str(pk["tflops_burst"]) + ")",
+            "class_share_of_step": ms / ms_total,
+            "conv_family": {"achieved": fam, "frac": fam / pk["tflops"], "launches_per_step": conv_launches / steps,
+                            "share_of_step": conv_ms / ms_total}}
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -299,7 +334,7 @@ def main():
     with ConvTimer(L) as ct:
         ct.register_real_cin(pipe.vae)
         ms_total = timed(step_resident, args.steps)
-        conv_flops, conv_ms, conv_launches = ct.result()
+        conv_flops, conv_ms, conv_launches, top = ct.result()
     launches = L.launch_count - l0
     ms_e2e = timed(step_e2e, args.steps) if not args.profile else ms_total
     clocks = sampler.stop() if rank == 0 else None
@@ -324,10 +359,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": host_clip.numel() * 4,
                     "d2h_bytes_per_step": host_out.numel() * 2},
             "gpu_launches": launches,
-            "roofline": {"bound": "tensor", "kernel": "umma_gemm_kernel<BN,conv> (tcgen05 implicit-GEMM CausalConv3d/Conv2d)",
-                         "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
-                         "traffic": None, "peak_source": pk["source"] + " (sustained cuBLAS bf16)",
-                         "launches_per_step": conv_launches / args.steps, "share_of_step": conv_ms / ms_total},
+            "roofline": roofline(pk, conv_flops, conv_ms, conv_launches, top, ms_total, args.steps),
         }
         if not args.no_cpu_baseline and not args.profile:
             try:

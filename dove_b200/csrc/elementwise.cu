@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
   const int vper = blockDim.x / vcols;
   const long long HW = static_cast<long long>(H) * W;
   const long long stride = static_cast<long long>(gridDim.x) * vper;
-  constexpr int U = 4;                       // voxels in flight per thread (memory-level parallelism)
+  constexpr int U = 8;                       // voxels in flight per thread (memory-level parallelism)
   for (long long vox0 = static_cast<long long>(blockIdx.x) * vper + threadIdx.x / vcols; vox0 < nvox;
        vox0 += stride * U) {
     uint4 raw[U];
@@ -315,8 +315,10 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
 #pragma unroll
       for (int k = 0; k < 8; ++k) f[k] = bf16_round(f[k] * a[k] + b[k]);
       if (zy) {
-        const int tf = static_cast<int>(vox / HW);
-        const int rem = static_cast<int>(vox - tf * HW);
+        const unsigned voxu = static_cast<unsigned>(vox);        // nvox < 2^31 (checked on the host)
+        const unsigned HWu = static_cast<unsigned>(HW);
+        const int tf = static_cast<int>(voxu / HWu);
+        const int rem = static_cast<int>(voxu - tf * HWu);
         const int yh = rem / W, xw = rem - yh * W;
         int tz;
         if (T > 1 && (T & 1)) tz = (tf == 0) ? 0 : 1 + ((tf - 1) * (Tz - 1)) / (T - 1);
@@ -615,8 +617,9 @@ extern "C" int dove_gn_apply_bf16(const void* x, void* out, int T, int H, int W,
   DOVE_CHECK_ARG(T > 0 && H > 0 && W > 0 && C % 8 == 0 && C % groups == 0, "gn_apply: bad shape");
   DOVE_CHECK_ARG((zq_y == nullptr) == (zq_b == nullptr), "gn_apply: zq_y/zq_b must come together");
   DOVE_CHECK_ARG(256 % (C >> 3) == 0, "gn_apply: C/8 must divide 256 (C=%d)", C);
+  DOVE_CHECK_ARG(static_cast<long long>(T) * H * W < (1ll << 31), "gn_apply: too many voxels");
   const long long nvec = static_cast<long long>(T) * H * W * (C >> 3);
-  gn_apply_kernel<<<grid_for(nvec, 256, 8), 256, 0, ST(stream)>>>(
+  gn_apply_kernel<<<grid_for(nvec / 8 + 1, 256, 2), 256, 0, ST(stream)>>>(
       static_cast<const bf16*>(x), static_cast<bf16*>(out), T, H, W, C, groups, stats,
       static_cast<const bf16*>(gamma), static_cast<const bf16*>(beta), apply_silu, static_cast<const bf16*>(zq_y),
       static_cast<const bf16*>(zq_b), Tz, hz, wz);

@@ -160,29 +160,36 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint32_t v[32];
           tmem_ld32(t_row + c0, v);
           tmem_ld_wait();
+          // voxels c0+i (even lanes store it) and c0+i+1 (odd lanes): lane pairs swap one value so that every lane
+          // stores a packed (channel, channel+1) pair -> 64 contiguous bytes per voxel per half-warp.
+          // All residual loads are issued BEFORE any store (C and aux may alias, so the compiler would otherwise
+          // serialise load -> store -> load and expose one DRAM latency per voxel pair).
+          long long offs[16];
+          uint32_t res[16];
+          bool oks[16];
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            // voxels c0+i (even lanes store it) and c0+i+1 (odd lanes): lane pairs swap one value so that every
-            // lane stores a packed (channel, channel+1) pair -> 64 contiguous bytes per voxel per half-warp
-            const int vi = c0 + i + (lane & 1);
+          for (int i = 0; i < 16; ++i) {
+            const int vi = c0 + 2 * i + (lane & 1);
             const int h = hy * p.th + (vi >> tw_shift), w = wx * p.tw + (vi & tw_mask);
-            const bool ok = (h < p.Ho) && (w < p.Wo);
+            oks[i] = (h < p.Ho) && (w < p.Wo);
             const long long row = (static_cast<long long>(t) * p.Ho + h) * p.Wo + w;
-            float a = bf16_round(__uint_as_float(v[i]) + bias_v);
-            float b = bf16_round(__uint_as_float(v[i + 1]) + bias_v);
+            offs[i] = row * p.ldc + (ch & ~1);
+            res[i] = 0;
+            if (p.epi == DOVE_EPI_ADD && oks[i])
+              res[i] = *reinterpret_cast<const uint32_t*>(p.aux + row * p.ld_aux + (ch & ~1));
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float a = bf16_round(__uint_as_float(v[2 * i]) + bias_v);
+            const float b = bf16_round(__uint_as_float(v[2 * i + 1]) + bias_v);
             const float send = (lane & 1) ? a : b;
             const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
             float lo = (lane & 1) ? recv : a;     // channel (ch & ~1)
             float hi = (lane & 1) ? b : recv;     // channel (ch | 1)
-            if (ok) {
-              const long long off = row * p.ldc + (ch & ~1);
-              if (p.epi == DOVE_EPI_ADD) {
-                const float2 x2 = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p.aux + row * p.ld_aux + (ch & ~1)));
-                lo += x2.x;
-                hi += x2.y;
-              }
-              *reinterpret_cast<uint32_t*>(p.C + off) = pack_bf16x2(lo, hi);
-            }
+            const float2 x2 = unpack_bf16x2(res[i]);
+            lo += x2.x;
+            hi += x2.y;
+            if (oks[i]) *reinterpret_cast<uint32_t*>(p.C + offs[i]) = pack_bf16x2(lo, hi);
           }
         }
         tc_fence_before();
