@@ -16,6 +16,8 @@ namespace dove {
 int conv2cta_dispatch(const void* x, const void* w, int Tout, int Hin, int Win, int Cin, int Cout_pad, int kt,
                       int Ho, int Wo, GemmParams p, cudaStream_t st);
 int get_option_conv2cta();
+int gemm2cta_launch(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K, GemmParams p,
+                    cudaStream_t st);
 
 template <int BN>
 struct GemmCfg {
@@ -344,6 +346,8 @@ extern "C" int dove_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
   p.n_valid = N;
   p.out_mode = 0;
   p.rows_total = M;
+  if (get_option_conv2cta() != 0 && N % 256 == 0 && M >= 2048)   // large GEMMs: CTA-pair kernel, 256 x 256 tiles
+    return gemm2cta_launch(A, lda, W, ldw, M, N, K, p, static_cast<cudaStream_t>(stream));
   return dispatch_bn<false>(bn, tmA, tmB, p, static_cast<cudaStream_t>(stream));
 }
 

@@ -1,0 +1,164 @@
+// CTA-pair (cta_group::2) dense GEMM: C[M,N] = epi(A[M,K] W[N,K]^T + bias) with 256 x 256 pair tiles.
+// One tcgen05.mma.cta_group::2 instruction spans two SMs (M = 256: CTA r owns rows r*128..r*128+127 of the pair
+// tile) and N = 256; each SM stages its own 128 A rows and only HALF of the weight tile (128 of the 256 N rows), so
+// shared-memory traffic per FLOP is 2/3 of the 1-CTA 128 x 256 tile and the tensor pipe is no longer operand-bound.
+// Same roles as gemm.cu: warp 0 TMA producer (both CTAs), warp 1 TMEM owner (both) + MMA issuer (leader),
+// warps 2..9 epilogue (both CTAs).  "full" barriers live in the leader; "empty" barriers are released in both CTAs by
+// multicast tcgen05.commit; accumulators are double-buffered in TMEM (2 x 256 columns).
+#include "gemm_common.cuh"
+
+namespace dove {
+
+struct Gemm2Cfg {
+  static constexpr int STAGES = 6;
+  static constexpr uint32_t A_BYTES = 128 * 128;
+  static constexpr uint32_t B_BYTES = 128 * 128;     // half of the 256-row weight tile
+  static constexpr size_t SMEM = 1024 + STAGES * (A_BYTES + B_BYTES) + 256;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
+gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const GemmParams p) {
+  using Cfg = Gemm2Cfg;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int BN = 256, CH = 32;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::B_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int total_tiles = p.num_m_tiles * p.num_n_tiles;     // m-tiles are 256-row pair tiles
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 16); }
+    fence_mbar_init();
+  }
+  __syncwarp();
+  if (warp == 1) tmem_alloc_2cta<512>(tmem_ptr);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0 && lane == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = pair; tile < total_tiles; tile += npairs) {
+      const int mt = tile / p.num_n_tiles, nt = tile % p.num_n_tiles;
+      const int row0 = mt * 256 + static_cast<int>(rank) * 128;
+      const int n0 = nt * BN + static_cast<int>(rank) * 128;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        const uint32_t fb = mapa_shared(smem_u32(&full[stage]), 0);
+        if (rank == 0) mbar_expect_tx(&full[stage], 2 * (Cfg::A_BYTES + Cfg::B_BYTES));
+        tma_load_2d_2cta(sA + stage * Cfg::A_BYTES, &tmA, fb, kb * 64, row0);
+        tma_load_2d_2cta(sB + stage * Cfg::B_BYTES, &tmB, fb, kb * 64, n0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0 && rank == 0) {
+    constexpr uint32_t idesc = umma_idesc_bf16(256, BN, 0, 0);
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    for (int tile = pair; tile < total_tiles; tile += npairs) {
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint64_t adesc = umma_desc_sw128(smem_u32(sA + stage * Cfg::A_BYTES));
+        const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + stage * Cfg::B_BYTES));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_ss_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+        umma_commit_2cta(&empty[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit_2cta(&tfull[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else if (warp >= 2) {
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int r_in_tile = q * 32 + lane;
+    const uint32_t tempty_leader0 = mapa_shared(smem_u32(&tempty[0]), 0);
+    const uint32_t tempty_leader1 = mapa_shared(smem_u32(&tempty[1]), 0);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < total_tiles; tile += npairs) {
+      const int mt = tile / p.num_n_tiles, nt = tile % p.num_n_tiles;
+      const long long row = static_cast<long long>(mt) * 256 + static_cast<int>(rank) * 128 + r_in_tile;
+      const bool valid = row < p.M;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      const bf16* gate = (p.epi == DOVE_EPI_GATED_RES) ? (row < p.split_row ? p.gate0 : p.gate1) : nullptr;
+#pragma unroll 1
+      for (int c0 = half * CH; c0 < BN; c0 += 2 * CH) {
+        uint32_t v[CH];
+        tmem_ld32(t_row + c0, v);
+        tmem_ld_wait();
+        if (valid) epilogue_chunk<CH>(p, v, row, nt * BN + c0, gate);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta<512>(tmem_base);
+  }
+}
+
+int gemm2cta_launch(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K, GemmParams p,
+                    cudaStream_t st) {
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
+    uint64_t strides[1] = {static_cast<uint64_t>(lda) * 2};
+    uint32_t box[2] = {64, 128};
+    if (int e = make_tmap_bf16(&tmA, A, 2, dims, strides, box, nullptr)) return e;
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+    uint64_t strides[1] = {static_cast<uint64_t>(ldw) * 2};
+    uint32_t box[2] = {64, 128};
+    if (int e = make_tmap_bf16(&tmB, W, 2, dims, strides, box, nullptr)) return e;
+  }
+  p.num_m_tiles = (M + 255) / 256;
+  p.num_n_tiles = N / 256;
+  p.num_kb = K / 64;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(Gemm2Cfg::SMEM));
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gemm2cta_kernel)");
+    attr_set = true;
+  }
+  const int total = p.num_m_tiles * p.num_n_tiles;
+  const int max_pairs = num_sms() / 2;
+  const int pairs = total < max_pairs ? total : max_pairs;
+  gemm2cta_kernel<<<pairs * 2, 320, Gemm2Cfg::SMEM, st>>>(tmA, tmB, p);
+  DOVE_LAUNCH_CHECK("gemm2cta_kernel");
+  return DOVE_OK;
+}
+
+}  // namespace dove

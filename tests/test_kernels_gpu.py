@@ -28,7 +28,8 @@ def randn(*s, std=1.0, seed=0):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 256, 128), (129, 64, 64), (200, 16, 64), (777, 32, 192),
-                                   (1000, 128, 3072), (2500, 3072, 1024), (1111, 768, 256)])
+                                   (1000, 128, 3072), (2500, 3072, 1024), (1111, 768, 256),
+                                   (4097, 512, 256), (2304, 256, 64)])   # M >= 2048, N % 256 == 0: CTA-pair kernel
 @pytest.mark.parametrize("epi", [0, 1, 2, 3])
 def test_gemm(L, M, N, K, epi):
     a = randn(M, K, seed=1)

@@ -208,7 +208,7 @@ def test_runner_chunks_and_tiles_real_pipe(env):
     pipe = m.b200_pipe(env["vsd"], env["dsd"], env["cfg"])
     emb = synthetic_prompt_embedding()
     torch.manual_seed(5)
-    video = torch.rand(1, 3, 41, 96, 96) * 2 - 1
+    video = torch.rand(1, 3, 49, 96, 96) * 2 - 1     # chunks (0,25),(17,49): the short tail is merged (ref :274-277)
     kw = dict(chunk_len=25, overlap_t=8, tile_size_hw=(64, 64), overlap_hw=(32, 32))
     fn = make_process_fn(pipe, emb)
     out = super_resolve(video, fn, noise_mode="per_unit", seed=42, **kw)
@@ -221,7 +221,7 @@ def test_runner_chunks_and_tiles_real_pipe(env):
         ref[:, :, g["out_t_start"]:g["out_t_end"], g["out_h_start"]:g["out_h_end"], g["out_w_start"]:g["out_w_end"]] = \
             r[:, :, g["valid_t_start"]:g["valid_t_end"], g["valid_h_start"]:g["valid_h_end"], g["valid_w_start"]:g["valid_w_end"]]
     torch.cuda.synchronize()
-    assert out.shape == (1, 3, 41, 96, 96) and torch.equal(out, ref)
+    assert out.shape == (1, 3, 49, 96, 96) and torch.equal(out, ref)
 
 
 def test_from_pretrained_diffusers_layout(env, tmp_path):
