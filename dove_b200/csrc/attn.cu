@@ -36,6 +36,26 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// packed fp32x2 arithmetic (sm_100): one issue slot for two lanes of the softmax's scale-subtract and row-sum
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 __global__ void __launch_bounds__(192, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -162,16 +182,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
         m_used = m_new;
       }
       // exponentials first (MUFU-bound phase, overlaps PV_{j-1} still running on the tensor pipe) ...
-      float lsum = 0.f;
       const float neg_m = -m_used;
+      const uint64_t sl2_2 = pack_f32x2(sl2, sl2), negm_2 = pack_f32x2(neg_m, neg_m);
+      uint64_t lsum2a = 0ull, lsum2b = 0ull;      // two packed accumulators (4 independent add chains)
       uint32_t pk[64];
 #pragma unroll
-      for (int i = 0; i < 64; ++i) {
-        const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), sl2, neg_m));
-        const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), sl2, neg_m));
-        lsum += p0 + p1;
+      for (int i = 0; i < 64; i += 2) {
+        const uint64_t xa = fma_f32x2(pack_f32x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), sl2_2, negm_2);
+        const uint64_t xb = fma_f32x2(pack_f32x2(__uint_as_float(v[2 * i + 2]), __uint_as_float(v[2 * i + 3])), sl2_2, negm_2);
+        float a0, a1, b0, b1;
+        unpack_f32x2(xa, a0, a1);
+        unpack_f32x2(xb, b0, b1);
+        // (emulating part of the exp2s with an FMA-pipe polynomial was measured 39 % SLOWER here: the softmax warps are
+        //  as issue-limited as they are MUFU-limited, profiles/r01_microbench.txt)
+        const float p0 = ex2_approx(a0), p1 = ex2_approx(a1), p2 = ex2_approx(b0), p3 = ex2_approx(b1);
+        lsum2a = add_f32x2(lsum2a, pack_f32x2(p0, p1));
+        lsum2b = add_f32x2(lsum2b, pack_f32x2(p2, p3));
         pk[i] = pack_bf16x2(p0, p1);
+        pk[i + 1] = pack_bf16x2(p2, p3);
       }
+      float ls0, ls1, ls2, ls3;
+      unpack_f32x2(lsum2a, ls0, ls1);
+      unpack_f32x2(lsum2b, ls2, ls3);
+      const float lsum = (ls0 + ls1) + (ls2 + ls3);
       // ... then wait for PV_{j-1}: the P buffer is free and O is stable from here on
       if (j > 0) {
         mbar_wait(pv_done, (j - 1) & 1);
