@@ -267,14 +267,19 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, int nblock
   }
 }
 
-// grid*block is a multiple of C/8, so every thread keeps ONE 8-channel column for its whole grid-stride loop and
-// the affine coefficients a = rstd*gamma, b = beta - mean*a are computed once per thread.
+// One image row (t, y) per block iteration; 256 % (C/8) == 0, so every thread keeps ONE 8-channel column for the
+// whole kernel and the affine coefficients a = rstd*gamma, b = beta - mean*a are computed once per thread.  All
+// divisions are per ROW (frame / row / nearest-neighbour source row of the SpatialNorm3D latent); the per-voxel
+// index math is shifts and adds (the x upsampling ratio is a power of two in the CogVideoX decoder; a generic
+// divide is kept for other ratios).
+template <int U>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int T,
                                                        int H, int W, int C, int groups,
                                                        const float* __restrict__ stats,
                                                        const bf16* __restrict__ gamma, const bf16* __restrict__ beta,
                                                        int apply_silu, const bf16* __restrict__ zy,
-                                                       const bf16* __restrict__ zb, int Tz, int hz, int wz) {
+                                                       const bf16* __restrict__ zb, int Tz, int hz, int wz,
+                                                       int x_shift) {
   const int vcols = C >> 3;
   const int cpg = C / groups;
   const int vcol = threadIdx.x % vcols;
@@ -292,51 +297,53 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
       b[k] = bt[k] - mean * a[k];
     }
   }
-  const long long nvox = static_cast<long long>(T) * H * W;
-  const int vper = blockDim.x / vcols;
-  const long long HW = static_cast<long long>(H) * W;
-  const long long stride = static_cast<long long>(gridDim.x) * vper;
-  constexpr int U = 8;                       // voxels in flight per thread (memory-level parallelism)
-  for (long long vox0 = static_cast<long long>(blockIdx.x) * vper + threadIdx.x / vcols; vox0 < nvox;
-       vox0 += stride * U) {
-    uint4 raw[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long vox = vox0 + u * stride;
-      if (vox < nvox) raw[u] = *reinterpret_cast<const uint4*>(x + (vox * vcols + vcol) * 8);
+  const int vper = 256 / vcols;                 // voxels of a row covered per block pass
+  const int xw0 = threadIdx.x / vcols;
+  const int rows = T * H;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int tf = row / H, yh = row - tf * H;
+    const bf16* xr = x + static_cast<long long>(row) * W * C + c0;
+    bf16* orow = out + static_cast<long long>(row) * W * C + c0;
+    const bf16* zyr = nullptr;
+    const bf16* zbr = nullptr;
+    if (zy) {
+      int tz;
+      if (T > 1 && (T & 1)) tz = (tf == 0) ? 0 : 1 + ((tf - 1) * (Tz - 1)) / (T - 1);
+      else tz = (tf * Tz) / T;
+      const int yz = (yh * hz) / H;
+      const long long zo = (static_cast<long long>(tz) * hz + yz) * wz * C + c0;
+      zyr = zy + zo;
+      zbr = zb + zo;
     }
+    for (int xw = xw0; xw < W; xw += vper * U) {
+      uint4 raw[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long vox = vox0 + u * stride;
-      if (vox >= nvox) break;
-      const long long i = vox * vcols + vcol;
-      float f[8];
-      unpack8(raw[u], f);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) f[k] = bf16_round(f[k] * a[k] + b[k]);
-      if (zy) {
-        const unsigned voxu = static_cast<unsigned>(vox);        // nvox < 2^31 (checked on the host)
-        const unsigned HWu = static_cast<unsigned>(HW);
-        const int tf = static_cast<int>(voxu / HWu);
-        const int rem = static_cast<int>(voxu - tf * HWu);
-        const int yh = rem / W, xw = rem - yh * W;
-        int tz;
-        if (T > 1 && (T & 1)) tz = (tf == 0) ? 0 : 1 + ((tf - 1) * (Tz - 1)) / (T - 1);
-        else tz = (tf * Tz) / T;
-        const int yz = (yh * hz) / H;
-        const int xz = (xw * wz) / W;
-        const long long zoff = ((static_cast<long long>(tz) * hz + yz) * wz + xz) * C + c0;
-        float yv[8], bv[8];
-        unpack8(*reinterpret_cast<const uint4*>(zy + zoff), yv);
-        unpack8(*reinterpret_cast<const uint4*>(zb + zoff), bv);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) f[k] = bf16_round(bf16_round(f[k] * yv[k]) + bv[k]);
+      for (int u = 0; u < U; ++u) {
+        const int xx = xw + u * vper;
+        if (xx < W) raw[u] = *reinterpret_cast<const uint4*>(xr + static_cast<long long>(xx) * C);
       }
-      if (apply_silu) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) f[k] = silu_f(f[k]);
+      for (int u = 0; u < U; ++u) {
+        const int xx = xw + u * vper;
+        if (xx >= W) break;
+        float f[8];
+        unpack8(raw[u], f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = bf16_round(f[k] * a[k] + b[k]);
+        if (zy) {
+          const int xz = x_shift >= 0 ? (xx >> x_shift) : (xx * wz) / W;
+          float yv[8], bv[8];
+          unpack8(*reinterpret_cast<const uint4*>(zyr + static_cast<long long>(xz) * C), yv);
+          unpack8(*reinterpret_cast<const uint4*>(zbr + static_cast<long long>(xz) * C), bv);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) f[k] = bf16_round(bf16_round(f[k] * yv[k]) + bv[k]);
+        }
+        if (apply_silu) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) f[k] = silu_f(f[k]);
+        }
+        *reinterpret_cast<uint4*>(orow + static_cast<long long>(xx) * C) = pack8(f);
       }
-      *reinterpret_cast<uint4*>(out + i * 8) = pack8(f);
     }
   }
 }
@@ -619,10 +626,20 @@ extern "C" int dove_gn_apply_bf16(const void* x, void* out, int T, int H, int W,
   DOVE_CHECK_ARG(256 % (C >> 3) == 0, "gn_apply: C/8 must divide 256 (C=%d)", C);
   DOVE_CHECK_ARG(static_cast<long long>(T) * H * W < (1ll << 31), "gn_apply: too many voxels");
   const long long nvec = static_cast<long long>(T) * H * W * (C >> 3);
-  gn_apply_kernel<<<grid_for(nvec / 8 + 1, 256, 2), 256, 0, ST(stream)>>>(
-      static_cast<const bf16*>(x), static_cast<bf16*>(out), T, H, W, C, groups, stats,
-      static_cast<const bf16*>(gamma), static_cast<const bf16*>(beta), apply_silu, static_cast<const bf16*>(zq_y),
-      static_cast<const bf16*>(zq_b), Tz, hz, wz);
+  int x_shift = -1;                               // log2(W / wz) when the x ratio is a power of two
+  if (zq_y && wz > 0 && W % wz == 0) {
+    const int r = W / wz;
+    if ((r & (r - 1)) == 0) {
+      x_shift = 0;
+      while ((1 << x_shift) < r) ++x_shift;
+    }
+  }
+  const int rows = T * H;
+  const int blocks = rows < num_sms() * 8 ? rows : num_sms() * 8;
+  gn_apply_kernel<4><<<blocks, 256, 0, ST(stream)>>>(
+      static_cast<const bf16*>(x), static_cast<bf16*>(out), T, H, W, C, groups, stats, static_cast<const bf16*>(gamma),
+      static_cast<const bf16*>(beta), apply_silu, static_cast<const bf16*>(zq_y), static_cast<const bf16*>(zq_b), Tz, hz,
+      wz, x_shift);
   DOVE_LAUNCH_CHECK("gn_apply_kernel");
   return DOVE_OK;
 }
