@@ -188,7 +188,7 @@ def cpu_reference_sample(seconds_budget, layers, steps=1, warmup=0, weights_from
         layers = max(1, min(layers, int((avail_gb * 0.5 - 3) / 0.53)))
     except Exception:
         pass
-    F, H, W = 9, 32, 32                       # 9-frame 32x32 crop (one VAE frame batch); CPU conv3d is very slow
+    F, H, W = 9, 64, 96                       # 9-frame 64x96 crop (one VAE frame batch), ~10-20 s on 32 threads
     vae = OracleAutoencoderKLCogVideoX()
     dit = OracleCogVideoXTransformer3DModel(num_layers=layers)
     t0 = time.time()
@@ -234,7 +234,7 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "cfg-2 33x768x1280 one-step VSR; CPU arm timed on a 9x32x32 crop (bounded sample)",
+            "config": {"workload": "cfg-2 33x768x1280 one-step VSR; CPU arm timed on a 9x64x96 crop (bounded sample)",
                        "layers": args.layers},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
