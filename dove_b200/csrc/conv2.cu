@@ -34,7 +34,7 @@ struct Conv2Cfg {
 template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 conv2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const GemmParams p, const int kt) {
+                const __grid_constant__ CUtensorMap tmP, const GemmParams p, const int kt) {
   using Cfg = Conv2Cfg<BN>;
   constexpr int SA = Cfg::SA, SB = Cfg::SB;
   constexpr int CH = 32;
@@ -87,8 +87,10 @@ conv2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int dt = g / (p.cin_blocks * 3);
         mbar_wait(&a_empty[sa], pa ^ 1);
         if (rank == 0) mbar_expect_tx(&a_full[sa], 2 * Cfg::A_BOX_BYTES);
-        tma_load_4d_2cta(sA + sa * Cfg::A_SLOT, &tmA, mapa_shared(smem_u32(&a_full[sa]), 0), cb * 64, w0 - 1,
-                         h + dh - 1, t + dt);
+        int f = t + dt;
+        const CUtensorMap* src = conv_frame_src(p, &tmA, &tmP, f);
+        tma_load_4d_2cta(sA + sa * Cfg::A_SLOT, src, mapa_shared(smem_u32(&a_full[sa]), 0), cb * 64, w0 - 1,
+                         h + dh - 1, f);
         if (++sa == SA) { sa = 0; pa ^= 1; }
 #pragma unroll 1
         for (int dw = 0; dw < 3; ++dw) {
@@ -178,8 +180,8 @@ conv2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 template <int BN>
-static int launch_conv2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int kt,
-                        cudaStream_t st) {
+static int launch_conv2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmP, const GemmParams& p,
+                        int kt, cudaStream_t st) {
   using Cfg = Conv2Cfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -191,17 +193,16 @@ static int launch_conv2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ge
   const int total = p.num_m_tiles * p.num_n_tiles;
   const int max_pairs = num_sms() / 2;
   const int pairs = total < max_pairs ? total : max_pairs;
-  conv2cta_kernel<BN><<<pairs * 2, 320, Cfg::SMEM, st>>>(tmA, tmB, p, kt);
+  conv2cta_kernel<BN><<<pairs * 2, 320, Cfg::SMEM, st>>>(tmA, tmB, tmP, p, kt);
   DOVE_LAUNCH_CHECK("conv2cta_kernel");
   return DOVE_OK;
 }
 
 // Called from dove_conv_cl_bf16 for stride-1 3x3(x3) convs on wide images.  Returns DOVE_OK or an error.
-int conv2cta_dispatch(const void* x, const void* w, int Tout, int Hin, int Win, int Cin, int Cout_pad, int kt,
-                      int Ho, int Wo, GemmParams p, cudaStream_t st) {
+int conv2cta_dispatch(const void* x, const void* x_prev, int Tin, const void* w, int Tout, int Hin, int Win, int Cin,
+                      int Cout_pad, int kt, int Ho, int Wo, GemmParams p, cudaStream_t st) {
   const int bn = (Cout_pad % 256 == 0) ? 256 : 128;
-  const int Tin = Tout + kt - 1;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmP;
   {
     uint64_t dims[4] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(Win), static_cast<uint64_t>(Hin),
                         static_cast<uint64_t>(Tin)};
@@ -209,6 +210,11 @@ int conv2cta_dispatch(const void* x, const void* w, int Tout, int Hin, int Win, 
                            static_cast<uint64_t>(Hin) * Win * Cin * 2};
     uint32_t box[4] = {64, 130, 1, 1};
     if (int e = make_tmap_bf16(&tmA, x, 4, dims, strides, box, nullptr)) return e;
+    tmP = tmA;
+    if (x_prev) {
+      dims[3] = 2;
+      if (int e = make_tmap_bf16(&tmP, x_prev, 4, dims, strides, box, nullptr)) return e;
+    }
   }
   const int Ktot = kt * 9 * Cin;
   {
@@ -232,7 +238,7 @@ int conv2cta_dispatch(const void* x, const void* w, int Tout, int Hin, int Win, 
     p.band_h = bh;
   }
   p.cin_blocks = Cin / 64;
-  return bn == 256 ? launch_conv2<256>(tmA, tmB, p, kt, st) : launch_conv2<128>(tmA, tmB, p, kt, st);
+  return bn == 256 ? launch_conv2<256>(tmA, tmB, tmP, p, kt, st) : launch_conv2<128>(tmA, tmB, tmP, p, kt, st);
 }
 
 }  // namespace dove

@@ -13,8 +13,8 @@
 
 namespace dove {
 
-int conv2cta_dispatch(const void* x, const void* w, int Tout, int Hin, int Win, int Cin, int Cout_pad, int kt,
-                      int Ho, int Wo, GemmParams p, cudaStream_t st);
+int conv2cta_dispatch(const void* x, const void* x_prev, int Tin, const void* w, int Tout, int Hin, int Win, int Cin,
+                      int Cout_pad, int kt, int Ho, int Wo, GemmParams p, cudaStream_t st);
 int get_option_conv2cta();
 int gemm2cta_launch(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K, GemmParams p,
                     cudaStream_t st);
@@ -37,7 +37,7 @@ struct GemmCfg {
 template <int BN, bool kConv, bool kTrans = false>
 __global__ void __launch_bounds__(320, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmP, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int CH = Cfg::CH;
@@ -96,8 +96,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int dw = tap % p.kw;
           const int dh = (tap / p.kw) % p.kh;
           const int dt = tap / (p.kw * p.kh);
-          tma_load_4d(kTrans ? sB + stage * Cfg::B_BYTES : sA + stage * Cfg::A_BYTES, &tmA, &full[stage], c0,
-                      w0 * p.stride + dw - p.pad, h0 * p.stride + dh - p.pad, t + dt);
+          int f = t + dt;
+          const CUtensorMap* src = conv_frame_src(p, &tmA, &tmP, f);
+          tma_load_4d(kTrans ? sB + stage * Cfg::B_BYTES : sA + stage * Cfg::A_BYTES, src, &full[stage], c0,
+                      w0 * p.stride + dw - p.pad, h0 * p.stride + dh - p.pad, f);
         } else {
           tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], kb * 64, mt * 128);
         }
@@ -244,7 +246,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 template <int BN, bool kConv>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmP, const GemmParams& p,
+                       cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;   // idempotent; benign race
   if (!attr_set) {
@@ -255,12 +258,13 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   }
   const int total = p.num_m_tiles * p.num_n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
-  umma_gemm_kernel<BN, kConv><<<grid, 320, Cfg::SMEM, st>>>(tmA, tmB, p);
+  umma_gemm_kernel<BN, kConv><<<grid, 320, Cfg::SMEM, st>>>(tmA, tmB, tmP, p);
   DOVE_LAUNCH_CHECK("umma_gemm_kernel");
   return DOVE_OK;
 }
 
-static int launch_conv_trans(const CUtensorMap& tmX, const CUtensorMap& tmW, const GemmParams& p, cudaStream_t st) {
+static int launch_conv_trans(const CUtensorMap& tmX, const CUtensorMap& tmW, const CUtensorMap& tmP, const GemmParams& p,
+                             cudaStream_t st) {
   using Cfg = GemmCfg<256>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -271,20 +275,20 @@ static int launch_conv_trans(const CUtensorMap& tmX, const CUtensorMap& tmW, con
   }
   const int total = p.num_m_tiles * p.num_n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
-  umma_gemm_kernel<256, true, true><<<grid, 320, Cfg::SMEM, st>>>(tmX, tmW, p);
+  umma_gemm_kernel<256, true, true><<<grid, 320, Cfg::SMEM, st>>>(tmX, tmW, tmP, p);
   DOVE_LAUNCH_CHECK("umma_gemm_kernel<trans>");
   return DOVE_OK;
 }
 
 template <bool kConv>
-static int dispatch_bn(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
-                       cudaStream_t st) {
+static int dispatch_bn(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmP,
+                       const GemmParams& p, cudaStream_t st) {
   switch (bn) {
-    case 256: return launch_gemm<256, kConv>(tmA, tmB, p, st);
-    case 128: return launch_gemm<128, kConv>(tmA, tmB, p, st);
-    case 64: return launch_gemm<64, kConv>(tmA, tmB, p, st);
-    case 32: return launch_gemm<32, kConv>(tmA, tmB, p, st);
-    case 16: return launch_gemm<16, kConv>(tmA, tmB, p, st);
+    case 256: return launch_gemm<256, kConv>(tmA, tmB, tmP, p, st);
+    case 128: return launch_gemm<128, kConv>(tmA, tmB, tmP, p, st);
+    case 64: return launch_gemm<64, kConv>(tmA, tmB, tmP, p, st);
+    case 32: return launch_gemm<32, kConv>(tmA, tmB, tmP, p, st);
+    case 16: return launch_gemm<16, kConv>(tmA, tmB, tmP, p, st);
   }
   return set_error(DOVE_E_BAD_ARG, "unsupported BN %d", bn);
 }
@@ -348,14 +352,26 @@ extern "C" int dove_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
   p.rows_total = M;
   if (get_option_conv2cta() != 0 && N % 256 == 0 && M >= 2048)   // large GEMMs: CTA-pair kernel, 256 x 256 tiles
     return gemm2cta_launch(A, lda, W, ldw, M, N, K, p, static_cast<cudaStream_t>(stream));
-  return dispatch_bn<false>(bn, tmA, tmB, p, static_cast<cudaStream_t>(stream));
+  return dispatch_bn<false>(bn, tmA, tmB, tmA, p, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int dove_conv_cl_bf16(const void* x, const void* w, const void* bias, void* y, int Tout, int Hin,
-                                 int Win, int Cin, int Cout_pad, int cout_valid, int64_t ldy, int kt, int kh,
-                                 int kw, int stride, int pad, int Ho, int Wo, int epilogue, const void* aux,
-                                 int64_t ld_aux, int out_mode, void* stream) {
+// cached != 0: causal 3x3x3 conv on the UN-padded frame batch x [Tout,H,W,Cin]; the two preceding frames come from
+// x_prev [2,H,W,Cin] (the conv cache) or, when x_prev is NULL, frame 0 is replicated (first frame batch).
+static int conv_impl(const void* x, const void* x_prev, int cached, const void* w, const void* bias, void* y, int Tout,
+                     int Hin, int Win, int Cin, int Cout_pad, int cout_valid, int64_t ldy, int kt, int kh, int kw,
+                     int stride, int pad, int Ho, int Wo, int epilogue, const void* aux, int64_t ld_aux, int out_mode,
+                     void* stream) {
   if (int e = ensure_init()) return e;
+  DOVE_CHECK_ARG(!cached || (kt == 3 && stride == 1), "conv: cached mode is for causal kt = 3, stride 1 convs");
+  const int t_shift = cached ? kt - 1 : 0;
+  const int has_prev = (cached && x_prev) ? 1 : 0;
+  const int Tin_all = cached ? Tout : Tout + kt - 1;      // frames present in x
+  auto make_prev_map = [&](CUtensorMap* tm, const uint32_t* box, const uint32_t* es) -> int {
+    uint64_t dims[4] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(Win), static_cast<uint64_t>(Hin), 2};
+    uint64_t strides[3] = {static_cast<uint64_t>(Cin) * 2, static_cast<uint64_t>(Win) * Cin * 2,
+                           static_cast<uint64_t>(Hin) * Win * Cin * 2};
+    return make_tmap_bf16(tm, x_prev, 4, dims, strides, box, es);
+  };
   DOVE_CHECK_ARG(Tout > 0 && Hin > 0 && Win > 0 && Ho > 0 && Wo > 0, "conv: empty problem");
   DOVE_CHECK_ARG(Cin % 64 == 0, "conv: Cin=%d must be a multiple of 64 (pad channels)", Cin);
   DOVE_CHECK_ARG(Cout_pad % 16 == 0 && cout_valid <= Cout_pad, "conv: Cout_pad=%d must be a multiple of 16", Cout_pad);
@@ -385,7 +401,10 @@ extern "C" int dove_conv_cl_bf16(const void* x, const void* w, const void* bias,
       q.n_valid = cout_valid;
       q.out_mode = 0;
       q.rows_total = static_cast<long long>(Tout) * Ho * Wo;
-      return conv2cta_dispatch(x, w, Tout, Hin, Win, Cin, Cout_pad, kt, Ho, Wo, q, static_cast<cudaStream_t>(stream));
+      q.t_shift = t_shift;
+      q.has_prev = has_prev;
+      return conv2cta_dispatch(x, has_prev ? x_prev : nullptr, Tin_all, w, Tout, Hin, Win, Cin, Cout_pad, kt, Ho, Wo, q,
+                               static_cast<cudaStream_t>(stream));
     }
   }
   // 128-channel-out convs on large images: swapped operand roles (weights = M 128, voxels = N 256)
@@ -403,8 +422,8 @@ extern "C" int dove_conv_cl_bf16(const void* x, const void* w, const void* bias,
       }
     }
     const int tw = best_tw, th = 256 / tw;
-    const int Tin = Tout + kt - 1;
-    CUtensorMap tmX, tmW;
+    const int Tin = Tin_all;
+    CUtensorMap tmX, tmW, tmP;
     {
       uint64_t dims[4] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(Win), static_cast<uint64_t>(Hin),
                           static_cast<uint64_t>(Tin)};
@@ -412,6 +431,9 @@ extern "C" int dove_conv_cl_bf16(const void* x, const void* w, const void* bias,
                              static_cast<uint64_t>(Hin) * Win * Cin * 2};
       uint32_t box[4] = {64, static_cast<uint32_t>(tw), static_cast<uint32_t>(th), 1};
       if (int e = make_tmap_bf16(&tmX, x, 4, dims, strides, box, nullptr)) return e;
+      tmP = tmX;
+      if (has_prev)
+        if (int e = make_prev_map(&tmP, box, nullptr)) return e;
     }
     const int Ktot = kt * kh * kw * Cin;
     {
@@ -443,6 +465,8 @@ extern "C" int dove_conv_cl_bf16(const void* x, const void* w, const void* bias,
     q.cin_blocks = Cin / 64;
     q.stride = 1;
     q.pad = pad;
+    q.t_shift = t_shift;
+    q.has_prev = has_prev;
     q.epi = epilogue;
     q.C = static_cast<bf16*>(y);
     q.ldc = ldy;
@@ -452,7 +476,7 @@ extern "C" int dove_conv_cl_bf16(const void* x, const void* w, const void* bias,
     q.n_valid = cout_valid;
     q.out_mode = 0;
     q.rows_total = static_cast<long long>(Tout) * Ho * Wo;
-    return launch_conv_trans(tmX, tmW, q, static_cast<cudaStream_t>(stream));
+    return launch_conv_trans(tmX, tmW, tmP, q, static_cast<cudaStream_t>(stream));
   }
   const int bn = pick_bn(Cout_pad);
   // output tile geometry: tw x th = 128 voxels of one frame, tw a power of two minimising padded waste
@@ -468,8 +492,8 @@ extern "C" int dove_conv_cl_bf16(const void* x, const void* w, const void* bias,
     }
   }
   const int tw = best_tw, th = 128 / tw;
-  const int Tin = Tout + kt - 1;
-  CUtensorMap tmA, tmB;
+  const int Tin = Tin_all;
+  CUtensorMap tmA, tmB, tmP;
   {
     uint64_t dims[4] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(Win), static_cast<uint64_t>(Hin),
                         static_cast<uint64_t>(Tin)};
@@ -478,6 +502,9 @@ extern "C" int dove_conv_cl_bf16(const void* x, const void* w, const void* bias,
     uint32_t box[4] = {64, static_cast<uint32_t>(tw * stride), static_cast<uint32_t>(th * stride), 1};
     uint32_t es[4] = {1, static_cast<uint32_t>(stride), static_cast<uint32_t>(stride), 1};
     if (int e = make_tmap_bf16(&tmA, x, 4, dims, strides, box, es)) return e;
+    tmP = tmA;
+    if (has_prev)
+      if (int e = make_prev_map(&tmP, box, es)) return e;
   }
   const int Ktot = kt * kh * kw * Cin;
   {
@@ -509,6 +536,8 @@ extern "C" int dove_conv_cl_bf16(const void* x, const void* w, const void* bias,
   p.cin_blocks = Cin / 64;
   p.stride = stride;
   p.pad = pad;
+  p.t_shift = t_shift;
+  p.has_prev = has_prev;
   p.epi = epilogue;
   p.C = static_cast<bf16*>(y);
   p.ldc = ldy;
@@ -518,5 +547,20 @@ extern "C" int dove_conv_cl_bf16(const void* x, const void* w, const void* bias,
   p.n_valid = cout_valid;
   p.out_mode = out_mode;
   p.rows_total = out_mode == 1 ? ldy : static_cast<long long>(Tout) * Ho * Wo;
-  return dispatch_bn<true>(bn, tmA, tmB, p, static_cast<cudaStream_t>(stream));
+  return dispatch_bn<true>(bn, tmA, tmB, tmP, p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int dove_conv_cl_bf16(const void* x, const void* w, const void* bias, void* y, int Tout, int Hin,
+                                 int Win, int Cin, int Cout_pad, int cout_valid, int64_t ldy, int kt, int kh,
+                                 int kw, int stride, int pad, int Ho, int Wo, int epilogue, const void* aux,
+                                 int64_t ld_aux, int out_mode, void* stream) {
+  return conv_impl(x, nullptr, 0, w, bias, y, Tout, Hin, Win, Cin, Cout_pad, cout_valid, ldy, kt, kh, kw, stride, pad, Ho,
+                   Wo, epilogue, aux, ld_aux, out_mode, stream);
+}
+
+extern "C" int dove_conv3d_causal_bf16(const void* x, const void* x_prev, const void* w, const void* bias, void* y,
+                                       int T, int H, int W, int Cin, int Cout_pad, int cout_valid, int64_t ldy,
+                                       int epilogue, const void* aux, int64_t ld_aux, int out_mode, void* stream) {
+  return conv_impl(x, x_prev, 1, w, bias, y, T, H, W, Cin, Cout_pad, cout_valid, ldy, 3, 3, 3, 1, 1, H, W, epilogue, aux,
+                   ld_aux, out_mode, stream);
 }

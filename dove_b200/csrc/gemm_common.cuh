@@ -15,6 +15,8 @@ struct GemmParams {
   int Ho, Wo;
   int kh, kw, cin_blocks;
   int stride, pad;
+  int t_shift, has_prev;   // causal convs on an un-padded input: input frame = t + dt - t_shift; frames < 0 come
+                           // from the `prev` tensor map (the conv cache) or, without one, replicate frame 0
   // epilogue
   int epi;
   bf16* C;
@@ -51,6 +53,19 @@ __device__ __forceinline__ void conv_tile_coords(const GemmParams& p, int mt, in
   const int rr = r - t * pb;
   hy = b * p.band_h + rr / p.tiles_w;
   wx = rr % p.tiles_w;
+}
+
+// Source of input frame (t + dt) of a causal conv: the current frame batch, the cached 2 frames, or frame 0.
+__device__ __forceinline__ const CUtensorMap* conv_frame_src(const GemmParams& p, const CUtensorMap* cur,
+                                                             const CUtensorMap* prev, int& f) {
+  f -= p.t_shift;
+  if (f >= 0) return cur;
+  if (p.has_prev) {
+    f += 2;
+    return prev;
+  }
+  f = 0;
+  return cur;
 }
 
 // Fused epilogue for CH consecutive accumulator columns (n0 .. n0+CH) of output row `row`.

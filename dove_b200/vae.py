@@ -8,13 +8,13 @@ Mirror of the diffusers `AutoencoderKLCogVideoX` surface used by the reference:
   pipe.vae.device / dtype                                            :407
 
 Data layout in HBM: every activation is CHANNELS-LAST bf16 [T, H, W, C] (C contiguous) so a convolution tap is
-a plain 4-D TMA box [th, tw, 64ch] of the input; causal 3x3x3 convs read from a temporally padded buffer
-[T+2, H, W, C] whose 2 leading frames are the conv cache (CogVideoXCausalConv3d semantics).  Frame batching
+a plain 4-D TMA box [th, tw, 64ch] of the input; causal 3x3x3 convs take their 2 preceding frames from the conv cache (a
+view of the previous frame batch's input) through a second tensor map — no padded copy (CogVideoXCausalConv3d semantics).  Frame batching
 (8 pixel frames / 2 latent frames, first batch takes the remainder) and the per-conv cache follow
 `AutoencoderKLCogVideoX._encode/_decode`.
 
-Kernel sequence per ResnetBlock3D:  gn_stats -> gn_apply(+SiLU, writes straight into the padded conv input)
--> causal_pad_frames -> conv (tcgen05 implicit GEMM) -> gn_stats -> gn_apply -> causal_pad_frames ->
+Kernel sequence per ResnetBlock3D:  gn_stats -> gn_apply(+SiLU) -> causal conv (tcgen05 implicit GEMM, cache frames
+through a second tensor map) -> gn_stats -> gn_apply ->
 [1x1x1 shortcut GEMM] -> conv with the residual add fused in the epilogue.
 """
 from __future__ import annotations
@@ -167,10 +167,11 @@ class AutoencoderKLCogVideoX:
         return torch.empty(*shape, dtype=BF, device=self._device)
 
     def _norm_into_padded(self, norm, x, T, H, W, C, zq, silu=True):
-        """GroupNorm / SpatialNorm3D (+SiLU) of x [T,H,W,C] written into a fresh padded buffer [T+2,H,W,C]."""
+        """GroupNorm / SpatialNorm3D (+SiLU) of x [T,H,W,C] -> fresh conv input [T,H,W,C] (no temporal padding:
+        the causal conv reads its two preceding frames straight from the cache view, see _causal_conv)."""
         stats = torch.empty(64, dtype=torch.float32, device=self._device)
         L.gn_stats(x, C, 32, self.config.norm_eps, self._partial, stats)
-        xin = self._empty(T + 2, H, W, C)
+        xin = self._empty(T, H, W, C)
         zy = zb = None
         if norm.spatial:
             zq_cl, (Tz, hz, wz) = zq
@@ -179,22 +180,24 @@ class AutoencoderKLCogVideoX:
             zb = self._empty(Tz, hz, wz, C)
             L.gemm(zq_cl.view(nvz, 64), norm.conv_y.w, zy.view(nvz, C), norm.conv_y.b)
             L.gemm(zq_cl.view(nvz, 64), norm.conv_b.w, zb.view(nvz, C), norm.conv_b.b)
-        L.gn_apply(x, xin[2:], T, H, W, C, 32, stats, norm.gamma, norm.beta, silu, zy, zb)
+        L.gn_apply(x, xin, T, H, W, C, 32, stats, norm.gamma, norm.beta, silu, zy, zb)
         return xin
 
     def _causal_conv(self, conv, xin, T, H, W, cache, key, out=None, aux=None, out_mode=0, plane_stride=0):
-        """xin: padded [T+2,H,W,Cin_pad] with frames 2.. already written.  Fills the 2 leading frames from the
-        cache (or by replicating frame 0), saves the new cache, runs the conv."""
-        fe = H * W * conv.cin_pad
-        old = cache.get(key)
-        new = old if old is not None else self._empty(2, H, W, conv.cin_pad)
-        L.causal_pad_frames(xin, T, fe, old, new)
-        cache[key] = new
+        """xin: the conv's input frames [T,H,W,Cin_pad] of this frame batch.  Temporal padding is ZERO-COPY: the two
+        preceding frames are the cache = a view of the last two frames of the previous batch's xin (read by the kernel
+        through a second tensor map), or frame 0 replicated for the first batch (CogVideoXCausalConv3d semantics)."""
+        prev = cache.get(key)
         if out is None:
             out = self._empty(T, H, W, conv.cout_pad)
-        L.conv_cl(xin, conv.w, conv.b, out, T, 3, 3, 3, 1, 1, H, W, conv.cout,
-                  epilogue=L.EPI_ADD if aux is not None else L.EPI_BIAS, aux=aux, out_mode=out_mode,
-                  plane_stride=plane_stride)
+        L.conv3d_causal(xin, prev, conv.w, conv.b, out, conv.cout,
+                        epilogue=L.EPI_ADD if aux is not None else L.EPI_BIAS, aux=aux, out_mode=out_mode,
+                        plane_stride=plane_stride)
+        if T >= 2:
+            cache[key] = xin[T - 2:]                      # view: keeps xin alive until the next batch has used it
+        else:                                             # single-frame batch: [previous last frame, this frame]
+            first = prev[1:2] if prev is not None else xin[0:1]
+            cache[key] = torch.cat([first, xin[0:1]], dim=0).contiguous()
         return out
 
     def _resnet(self, r, x, T, H, W, zq, cache):
@@ -216,10 +219,10 @@ class AutoencoderKLCogVideoX:
     def _encoder_batch(self, pix, t0, t1, F, H, W, cache):
         """pix: [3, F, H, W] (fp32 or bf16) contiguous; frames t0..t1 -> moments [T', H/8, W/8, 32]."""
         T = t1 - t0
-        xin = self._empty(T + 2, H, W, 64)
+        xin = self._empty(T, H, W, 64)
         # per-channel planes of this frame batch are strided inside pix: gather through a contiguous view
         src = pix[:, t0:t1].contiguous()
-        L.pixels_to_cl(src, xin[2:], T, H, W, 64)
+        L.pixels_to_cl(src, xin, T, H, W, 64)
         x = self._causal_conv(self.enc_conv_in, xin, T, H, W, cache, "conv_in")
         del xin
         for bi, (res, down, compress_time) in enumerate(self.enc_down):
@@ -345,9 +348,9 @@ class AutoencoderKLCogVideoX:
         """z: [16, Tz_total, h, w] bf16; latent frames t0..t1 -> pixels written into out[3, F_out, 8h, 8w]."""
         T = t1 - t0
         zsrc = z[:, t0:t1].contiguous()
-        xin = self._empty(T + 2, h, w, 64)
-        L.ncthw_to_cl(zsrc, xin[2:], 16, T, h, w, 64, scale)
-        zq = (xin[2:], (T, h, w))                     # the (scaled) latent batch conditions every SpatialNorm3D
+        xin = self._empty(T, h, w, 64)
+        L.ncthw_to_cl(zsrc, xin, 16, T, h, w, 64, scale)
+        zq = (xin, (T, h, w))                     # the (scaled) latent batch conditions every SpatialNorm3D
         x = self._causal_conv(self.dec_conv_in, xin, T, h, w, cache, "conv_in")
         H, W = h, w
         for r in self.dec_mid:

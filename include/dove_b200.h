@@ -117,6 +117,16 @@ int dove_conv_cl_bf16(const void* x, const void* w, const void* bias, void* y, i
                       int Cout_pad, int cout_valid, int64_t ldy, int kt, int kh, int kw, int stride, int pad,
                       int Ho, int Wo, int epilogue, const void* aux, int64_t ld_aux, int out_mode, void* stream);
 
+/* Causal 3x3x3 convolution (CogVideoXCausalConv3d, stride 1, spatial zero pad 1) on the UN-padded frame batch
+ * x [T,H,W,Cin] with ZERO-COPY temporal padding: the two frames preceding x are read from x_prev [2,H,W,Cin] (the
+ * conv cache = the last two frames of the previous frame batch's input, typically a view of that buffer) through a
+ * second tensor map, or, when x_prev is NULL (first frame batch), input frame 0 is replicated — exactly
+ * `fake_context_parallel_forward` + `conv_cache` of diffusers, without materialising the padded tensor.
+ * Other arguments as dove_conv_cl_bf16. */
+int dove_conv3d_causal_bf16(const void* x, const void* x_prev, const void* w, const void* bias, void* y, int T, int H,
+                            int W, int Cin, int Cout_pad, int cout_valid, int64_t ldy, int epilogue, const void* aux,
+                            int64_t ld_aux, int out_mode, void* stream);
+
 /* GroupNorm statistics over a channels-last tensor [nvox, C]: mean/rstd per group -> stats[2*groups] fp32.
  * partial: workspace of dove_gn_partial_floats(nvox, groups) floats. */
 size_t dove_gn_partial_floats(int64_t nvox, int groups);

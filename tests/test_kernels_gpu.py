@@ -346,3 +346,29 @@ def test_preprocess_matches_reference_recipe(L):
     torch.cuda.synchronize()
     assert (out.cpu() - ref).abs().max().item() < 2e-6
     assert remove_padding_and_extra_frames(out, pf, ph, pw).shape == (1, 3, 10, 180, 280)
+
+
+@pytest.mark.parametrize("cin,cout,T,H,W", [(64, 64, 3, 12, 20), (128, 128, 2, 16, 256), (128, 256, 3, 6, 384),
+                                            (256, 128, 1, 24, 200), (512, 512, 2, 12, 20)])
+def test_conv3d_causal_zero_copy_cache(L, cin, cout, T, H, W):
+    """dove_conv3d_causal_bf16 (two preceding frames through a second tensor map / frame-0 replication) must be
+    bit-identical to the same kernel run on the materialised padded input, for the generic, swapped-operand and
+    CTA-pair kernels."""
+    x = randn(T, H, W, cin, seed=1)
+    prev = randn(2, H, W, cin, seed=2)
+    K = 27 * cin
+    w = randn(cout, K, std=K ** -0.5, seed=3)
+    bias = randn(cout, std=0.1, seed=4)
+    aux = randn(T, H, W, cout, seed=5)
+    for pv in (prev, None):
+        padded = torch.cat([pv, x], 0) if pv is not None else torch.cat([x[:1], x[:1], x], 0)
+        y_ref = torch.empty(T, H, W, cout, device="cuda", dtype=torch.bfloat16)
+        L.conv_cl(padded.contiguous(), w, bias, y_ref, T, 3, 3, 3, 1, 1, H, W, cout, epilogue=L.EPI_ADD, aux=aux)
+        y = torch.full_like(y_ref, float("nan"))
+        L.conv3d_causal(x, pv, w, bias, y, cout, epilogue=L.EPI_ADD, aux=aux)
+        torch.cuda.synchronize()
+        assert torch.equal(y, y_ref), (cin, cout, pv is None)
+    ref = conv_ref(torch.cat([prev, x], 0), w, bias, 3, 3, 3, 1, 1, cin, cout)
+    assert rel_l2(y_ref if False else y, rb(rb(conv_ref(torch.cat([x[:1], x[:1], x], 0), w, bias, 3, 3, 3, 1, 1, cin, cout))
+                                            + aux.float())) < TOL
+    del ref
