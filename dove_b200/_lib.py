@@ -44,9 +44,10 @@ _SIGS = {
     "dove_velocity_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_void_p]),
     "dove_conv_cl_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                   c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
-                                  c_int64, c_int, c_void_p]),
+                                  c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "dove_gn_finalize": (c_int, [c_void_p, c_int64, c_int, c_int, c_float, c_void_p, c_void_p]),
     "dove_conv3d_causal_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                                        c_int, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p]),
+                                        c_int, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "dove_gn_partial_floats": (c_size_t, [c_int64, c_int]),
     "dove_gn_stats_bf16": (c_int, [c_void_p, c_int64, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     "dove_gn_apply_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
@@ -198,8 +199,11 @@ def velocity(sample, noise, out, a, b):
 
 
 # ---------------------------------------------------------------------------------------------- VAE ops
+_gn_done = ctypes.c_int(0)
+
+
 def conv_cl(x, w, bias, y, Tout, kt, kh, kw, stride, pad, Ho, Wo, cout_valid, epilogue=EPI_BIAS, aux=None,
-            out_mode=0, plane_stride=0):
+            out_mode=0, plane_stride=0, gn_partial=None):
     """x [Tin,Hin,Win,Cin] channels-last; w [Cout_pad, kt*kh*kw*Cin]; y [Tout,Ho,Wo,ldy] (or planar)."""
     Tin, Hin, Win, Cin = x.shape
     assert Tin == Tout + kt - 1, (Tin, Tout, kt)
@@ -208,11 +212,13 @@ def conv_cl(x, w, bias, y, Tout, kt, kh, kw, stride, pad, Ho, Wo, cout_valid, ep
     assert x.dtype == torch.bfloat16 and x.is_contiguous() and y.dtype == torch.bfloat16
     _call("dove_conv_cl_bf16", _p(x), _p(_bf16c(w)), _p(bias), _p(y), Tout, Hin, Win, Cin, Cout_pad,
           cout_valid, ldy, kt, kh, kw, stride, pad, Ho, Wo, epilogue, _p(aux),
-          aux.shape[-1] if aux is not None else 0, out_mode, _stream())
-    return y
+          aux.shape[-1] if aux is not None else 0, out_mode, _p(gn_partial),
+          ctypes.byref(_gn_done) if gn_partial is not None else None, _stream())
+    return (y, bool(_gn_done.value)) if gn_partial is not None else y
 
 
-def conv3d_causal(x, x_prev, w, bias, y, cout_valid, epilogue=EPI_BIAS, aux=None, out_mode=0, plane_stride=0):
+def conv3d_causal(x, x_prev, w, bias, y, cout_valid, epilogue=EPI_BIAS, aux=None, out_mode=0, plane_stride=0,
+                  gn_partial=None):
     """Causal 3x3x3 conv on the un-padded frame batch x [T,H,W,Cin]; x_prev [2,H,W,Cin] (cache view) or None."""
     T, H, W, Cin = x.shape
     assert x.dtype == torch.bfloat16 and x.is_contiguous() and y.dtype == torch.bfloat16
@@ -220,8 +226,14 @@ def conv3d_causal(x, x_prev, w, bias, y, cout_valid, epilogue=EPI_BIAS, aux=None
         assert x_prev.shape == (2, H, W, Cin) and x_prev.is_contiguous() and x_prev.dtype == torch.bfloat16
     ldy = y.shape[-1] if out_mode == 0 else (plane_stride or T * H * W)
     _call("dove_conv3d_causal_bf16", _p(x), _p(x_prev), _p(_bf16c(w)), _p(bias), _p(y), T, H, W, Cin, w.shape[0],
-          cout_valid, ldy, epilogue, _p(aux), aux.shape[-1] if aux is not None else 0, out_mode, _stream())
-    return y
+          cout_valid, ldy, epilogue, _p(aux), aux.shape[-1] if aux is not None else 0, out_mode, _p(gn_partial),
+          ctypes.byref(_gn_done) if gn_partial is not None else None, _stream())
+    return (y, bool(_gn_done.value)) if gn_partial is not None else y
+
+
+def gn_finalize(partial, nvox, C, groups, eps, stats):
+    _call("dove_gn_finalize", _p(partial), nvox, C, groups, eps, _p(stats), _stream())
+    return stats
 
 
 def gn_partial_floats(nvox, groups=32):

@@ -50,6 +50,8 @@ conv2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
 
+  __shared__ float gn_red[8 * 64];                  // per-epilogue-warp GroupNorm partials [warp][group][2]
+  for (int i = threadIdx.x; i < 8 * 64; i += blockDim.x) gn_red[i] = 0.f;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();          // 0 = leader
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
@@ -161,7 +163,30 @@ conv2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         uint32_t v[CH];
         tmem_ld32(t_row + c0, v);
         tmem_ld_wait();
-        if (valid) epilogue_chunk<CH>(p, v, row, nt * BN + c0, nullptr);
+        if (p.gn_partial) {
+          float qs[8], qss[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) qs[i] = qss[i] = 0.f;
+          if (valid) epilogue_chunk<CH, true>(p, v, row, nt * BN + c0, nullptr, qs, qss);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              qs[i] += __shfl_xor_sync(0xffffffffu, qs[i], o);
+              qss[i] += __shfl_xor_sync(0xffffffffu, qss[i], o);
+            }
+          }
+          if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int g = (nt * BN + c0 + 4 * i) / p.gn_cpg;
+              gn_red[(warp - 2) * 64 + g * 2] += qs[i];
+              gn_red[(warp - 2) * 64 + g * 2 + 1] += qss[i];
+            }
+          }
+        } else if (valid) {
+          epilogue_chunk<CH>(p, v, row, nt * BN + c0, nullptr);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -173,6 +198,12 @@ conv2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncwarp();
   tc_fence_before();
   cluster_sync_all();
+  if (p.gn_partial && threadIdx.x < 64) {            // fixed-order combine of the 8 epilogue warps -> deterministic
+    float acc = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) acc += gn_red[w8 * 64 + threadIdx.x];
+    p.gn_partial[static_cast<long long>(blockIdx.x) * 64 + threadIdx.x] = acc;
+  }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc_2cta<Cfg::TMEM_COLS>(tmem_base);

@@ -203,7 +203,7 @@ __global__ void velocity_kernel(const bf16* __restrict__ sample, const bf16* __r
 }
 
 // ------------------------------------------------------------------------------------------------ GroupNorm
-constexpr int GN_MAX_BLOCKS = 1184;
+constexpr int GN_MAX_BLOCKS = 1184;   // == GN_PARTIAL_ROWS in gemm_common.cuh
 
 // x [nvox, C] channels-last.  thread -> fixed 8-channel vector column, strided over voxels.
 __global__ void __launch_bounds__(256) gn_partial_kernel(const bf16* __restrict__ x, long long nvox, int C,
@@ -613,6 +613,16 @@ extern "C" int dove_gn_stats_bf16(const void* x, int64_t nvox, int C, int groups
   DOVE_LAUNCH_CHECK("gn_partial_kernel");
   gn_finalize_kernel<<<1, 32 * 32, 0, ST(stream)>>>(partial, static_cast<int>(blocks), groups,
                                               static_cast<double>(nvox) * (C / groups), eps, stats);
+  DOVE_LAUNCH_CHECK("gn_finalize_kernel");
+  return DOVE_OK;
+}
+
+extern "C" int dove_gn_finalize(const float* partial, int64_t nvox, int C, int groups, float eps, float* stats,
+                               void* stream) {
+  if (int e = ensure_init()) return e;
+  DOVE_CHECK_ARG(groups == 32 && C % 32 == 0 && nvox > 0, "gn_finalize: bad shape");
+  gn_finalize_kernel<<<1, 32 * 32, 0, ST(stream)>>>(partial, GN_MAX_BLOCKS, groups,
+                                                   static_cast<double>(nvox) * (C / groups), eps, stats);
   DOVE_LAUNCH_CHECK("gn_finalize_kernel");
   return DOVE_OK;
 }

@@ -51,6 +51,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
 
+  __shared__ float gn_red[8 * 64];                  // per-epilogue-warp GroupNorm partials (kTrans only)
+  if (kTrans)
+    for (int i = threadIdx.x; i < 8 * 64; i += blockDim.x) gn_red[i] = 0.f;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.num_m_tiles * p.num_n_tiles;
@@ -147,6 +150,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int r_in_tile = q * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
+    float gn_s = 0.f, gn_ss = 0.f;          // kTrans: this thread's channel-pair sums over every voxel it stores
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int mt = tile / p.num_n_tiles, nt = tile % p.num_n_tiles;
       if (kTrans) {
@@ -193,7 +197,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const float2 x2 = unpack_bf16x2(res[i]);
             lo += x2.x;
             hi += x2.y;
-            if (oks[i]) *reinterpret_cast<uint32_t*>(p.C + offs[i]) = pack_bf16x2(lo, hi);
+            if (oks[i]) {
+              const uint32_t packed = pack_bf16x2(lo, hi);
+              *reinterpret_cast<uint32_t*>(p.C + offs[i]) = packed;
+              const float2 fr = unpack_bf16x2(packed);
+              gn_s += fr.x + fr.y;
+              gn_ss += fr.x * fr.x + fr.y * fr.y;
+            }
           }
         }
         tc_fence_before();
@@ -236,9 +246,26 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (kTrans && p.gn_partial) {          // 4 lanes = one group of 4 channels (C = 128, 32 groups)
+      gn_s += __shfl_xor_sync(0xffffffffu, gn_s, 1);
+      gn_ss += __shfl_xor_sync(0xffffffffu, gn_ss, 1);
+      gn_s += __shfl_xor_sync(0xffffffffu, gn_s, 2);
+      gn_ss += __shfl_xor_sync(0xffffffffu, gn_ss, 2);
+      if ((lane & 3) == 0) {
+        const int g = q * 8 + (lane >> 2);
+        gn_red[(warp - 2) * 64 + g * 2] = gn_s;
+        gn_red[(warp - 2) * 64 + g * 2 + 1] = gn_ss;
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (kTrans && p.gn_partial && threadIdx.x < 64) {   // fixed-order combine of the 8 epilogue warps
+    float a8 = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) a8 += gn_red[w8 * 64 + threadIdx.x];
+    p.gn_partial[static_cast<long long>(blockIdx.x) * 64 + threadIdx.x] = a8;
+  }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
@@ -360,8 +387,9 @@ extern "C" int dove_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t
 static int conv_impl(const void* x, const void* x_prev, int cached, const void* w, const void* bias, void* y, int Tout,
                      int Hin, int Win, int Cin, int Cout_pad, int cout_valid, int64_t ldy, int kt, int kh, int kw,
                      int stride, int pad, int Ho, int Wo, int epilogue, const void* aux, int64_t ld_aux, int out_mode,
-                     void* stream) {
+                     float* gn_partial, int* gn_done, void* stream) {
   if (int e = ensure_init()) return e;
+  if (gn_done) *gn_done = 0;
   DOVE_CHECK_ARG(!cached || (kt == 3 && stride == 1), "conv: cached mode is for causal kt = 3, stride 1 convs");
   const int t_shift = cached ? kt - 1 : 0;
   const int has_prev = (cached && x_prev) ? 1 : 0;
@@ -403,6 +431,13 @@ static int conv_impl(const void* x, const void* x_prev, int cached, const void* 
       q.rows_total = static_cast<long long>(Tout) * Ho * Wo;
       q.t_shift = t_shift;
       q.has_prev = has_prev;
+      if (gn_partial && gn_done && cout_valid % 32 == 0) {
+        if (int e = check_cuda(cudaMemsetAsync(gn_partial, 0, sizeof(float) * GN_PARTIAL_ROWS * 64,
+                                               static_cast<cudaStream_t>(stream)), "gn partial memset")) return e;
+        q.gn_partial = gn_partial;
+        q.gn_cpg = cout_valid / 32;
+        *gn_done = 1;
+      }
       return conv2cta_dispatch(x, has_prev ? x_prev : nullptr, Tin_all, w, Tout, Hin, Win, Cin, Cout_pad, kt, Ho, Wo, q,
                                static_cast<cudaStream_t>(stream));
     }
@@ -467,6 +502,13 @@ static int conv_impl(const void* x, const void* x_prev, int cached, const void* 
     q.pad = pad;
     q.t_shift = t_shift;
     q.has_prev = has_prev;
+    if (gn_partial && gn_done) {
+      if (int e = check_cuda(cudaMemsetAsync(gn_partial, 0, sizeof(float) * GN_PARTIAL_ROWS * 64,
+                                             static_cast<cudaStream_t>(stream)), "gn partial memset")) return e;
+      q.gn_partial = gn_partial;
+      q.gn_cpg = 4;
+      *gn_done = 1;
+    }
     q.epi = epilogue;
     q.C = static_cast<bf16*>(y);
     q.ldc = ldy;
@@ -553,14 +595,15 @@ static int conv_impl(const void* x, const void* x_prev, int cached, const void* 
 extern "C" int dove_conv_cl_bf16(const void* x, const void* w, const void* bias, void* y, int Tout, int Hin,
                                  int Win, int Cin, int Cout_pad, int cout_valid, int64_t ldy, int kt, int kh,
                                  int kw, int stride, int pad, int Ho, int Wo, int epilogue, const void* aux,
-                                 int64_t ld_aux, int out_mode, void* stream) {
+                                 int64_t ld_aux, int out_mode, float* gn_partial, int* gn_done, void* stream) {
   return conv_impl(x, nullptr, 0, w, bias, y, Tout, Hin, Win, Cin, Cout_pad, cout_valid, ldy, kt, kh, kw, stride, pad, Ho,
-                   Wo, epilogue, aux, ld_aux, out_mode, stream);
+                   Wo, epilogue, aux, ld_aux, out_mode, gn_partial, gn_done, stream);
 }
 
 extern "C" int dove_conv3d_causal_bf16(const void* x, const void* x_prev, const void* w, const void* bias, void* y,
                                        int T, int H, int W, int Cin, int Cout_pad, int cout_valid, int64_t ldy,
-                                       int epilogue, const void* aux, int64_t ld_aux, int out_mode, void* stream) {
+                                       int epilogue, const void* aux, int64_t ld_aux, int out_mode, float* gn_partial,
+                                       int* gn_done, void* stream) {
   return conv_impl(x, x_prev, 1, w, bias, y, T, H, W, Cin, Cout_pad, cout_valid, ldy, 3, 3, 3, 1, 1, H, W, epilogue, aux,
-                   ld_aux, out_mode, stream);
+                   ld_aux, out_mode, gn_partial, gn_done, stream);
 }

@@ -30,7 +30,12 @@ struct GemmParams {
   int n_valid;    // columns stored
   int out_mode;   // 0 row-major [rows, ldc], 1 planar [n][rows_total]
   long long rows_total;
+  // fused GroupNorm statistics of the OUTPUT (consumed by the next GroupNorm): per-CTA partial sums
+  float* gn_partial;   // [GN_PARTIAL_ROWS][32 groups][2] (sum, sum of squares) or nullptr
+  int gn_cpg;          // channels per group of the output tensor
 };
+
+constexpr int GN_PARTIAL_ROWS = 1184;
 
 __device__ __forceinline__ float gelu_tanh_f(float x) {
   // 0.5*x*(1+tanh(sqrt(2/pi)*(x+0.044715x^3))), tanh(y) = 1 - 2/(exp(2y)+1)
@@ -69,9 +74,11 @@ __device__ __forceinline__ const CUtensorMap* conv_frame_src(const GemmParams& p
 }
 
 // Fused epilogue for CH consecutive accumulator columns (n0 .. n0+CH) of output row `row`.
-template <int CH>
+// kStats: also accumulates, per quad of 4 consecutive channels, the sum / sum of squares of the bf16-ROUNDED
+// outputs into qs[CH/4], qss[CH/4] (fused GroupNorm statistics).
+template <int CH, bool kStats = false>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t* v, long long row, int n0,
-                                               const bf16* gate) {
+                                               const bf16* gate, float* qs = nullptr, float* qss = nullptr) {
   float r[CH];
   if (p.bias) {
     const uint4* bp = reinterpret_cast<const uint4*>(p.bias + n0);
@@ -116,6 +123,14 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
           r[i + 1] += a2.y;
         }
       }
+    }
+  }
+  if (kStats) {
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      const float rr = bf16_round(r[i]);
+      qs[i >> 2] += rr;
+      qss[i >> 2] += rr * rr;
     }
   }
   if (p.out_mode == 0 && n0 + CH <= p.n_valid) {

@@ -166,11 +166,14 @@ class AutoencoderKLCogVideoX:
     def _empty(self, *shape):
         return torch.empty(*shape, dtype=BF, device=self._device)
 
-    def _norm_into_padded(self, norm, x, T, H, W, C, zq, silu=True):
+    def _norm_into_padded(self, norm, x, T, H, W, C, zq, silu=True, fused_stats=False):
         """GroupNorm / SpatialNorm3D (+SiLU) of x [T,H,W,C] -> fresh conv input [T,H,W,C] (no temporal padding:
         the causal conv reads its two preceding frames straight from the cache view, see _causal_conv)."""
         stats = torch.empty(64, dtype=torch.float32, device=self._device)
-        L.gn_stats(x, C, 32, self.config.norm_eps, self._partial, stats)
+        if fused_stats:      # the producing conv's epilogue already left per-CTA partial sums in self._partial
+            L.gn_finalize(self._partial, T * H * W, C, 32, self.config.norm_eps, stats)
+        else:
+            L.gn_stats(x, C, 32, self.config.norm_eps, self._partial, stats)
         xin = self._empty(T, H, W, C)
         zy = zb = None
         if norm.spatial:
@@ -183,29 +186,33 @@ class AutoencoderKLCogVideoX:
         L.gn_apply(x, xin, T, H, W, C, 32, stats, norm.gamma, norm.beta, silu, zy, zb)
         return xin
 
-    def _causal_conv(self, conv, xin, T, H, W, cache, key, out=None, aux=None, out_mode=0, plane_stride=0):
+    def _causal_conv(self, conv, xin, T, H, W, cache, key, out=None, aux=None, out_mode=0, plane_stride=0,
+                     want_stats=False):
         """xin: the conv's input frames [T,H,W,Cin_pad] of this frame batch.  Temporal padding is ZERO-COPY: the two
         preceding frames are the cache = a view of the last two frames of the previous batch's xin (read by the kernel
         through a second tensor map), or frame 0 replicated for the first batch (CogVideoXCausalConv3d semantics)."""
         prev = cache.get(key)
         if out is None:
             out = self._empty(T, H, W, conv.cout_pad)
-        L.conv3d_causal(xin, prev, conv.w, conv.b, out, conv.cout,
-                        epilogue=L.EPI_ADD if aux is not None else L.EPI_BIAS, aux=aux, out_mode=out_mode,
-                        plane_stride=plane_stride)
+        res = L.conv3d_causal(xin, prev, conv.w, conv.b, out, conv.cout,
+                              epilogue=L.EPI_ADD if aux is not None else L.EPI_BIAS, aux=aux, out_mode=out_mode,
+                              plane_stride=plane_stride, gn_partial=self._partial if want_stats else None)
+        has_stats = res[1] if want_stats else False
         if T >= 2:
             cache[key] = xin[T - 2:]                      # view: keeps xin alive until the next batch has used it
         else:                                             # single-frame batch: [previous last frame, this frame]
             first = prev[1:2] if prev is not None else xin[0:1]
             cache[key] = torch.cat([first, xin[0:1]], dim=0).contiguous()
-        return out
+        return (out, has_stats) if want_stats else out
 
-    def _resnet(self, r, x, T, H, W, zq, cache):
+    def _resnet(self, r, x, T, H, W, zq, cache, x_stats=False):
+        """-> (out, out_has_fused_stats).  x_stats: self._partial holds the GroupNorm partials of x (left there by the
+        conv that produced x); every conv here asks for the statistics of ITS output for the next norm."""
         cin, cout = r.conv1.cin, r.conv1.cout
-        xin = self._norm_into_padded(r.norm1, x, T, H, W, cin, zq)
-        h = self._causal_conv(r.conv1, xin, T, H, W, cache, r.name + ".conv1")
+        xin = self._norm_into_padded(r.norm1, x, T, H, W, cin, zq, fused_stats=x_stats)
+        h, h_stats = self._causal_conv(r.conv1, xin, T, H, W, cache, r.name + ".conv1", want_stats=True)
         del xin
-        xin2 = self._norm_into_padded(r.norm2, h, T, H, W, cout, zq)
+        xin2 = self._norm_into_padded(r.norm2, h, T, H, W, cout, zq, fused_stats=h_stats)
         del h
         if r.shortcut is not None:
             nv = T * H * W
@@ -213,7 +220,7 @@ class AutoencoderKLCogVideoX:
             L.gemm(x.view(nv, cin), r.shortcut.w, res.view(nv, cout), r.shortcut.b)
         else:
             res = x
-        return self._causal_conv(r.conv2, xin2, T, H, W, cache, r.name + ".conv2", aux=res)
+        return self._causal_conv(r.conv2, xin2, T, H, W, cache, r.name + ".conv2", aux=res, want_stats=True)
 
     # ---- encoder ----------------------------------------------------------------------------------
     def _encoder_batch(self, pix, t0, t1, F, H, W, cache):
@@ -223,11 +230,11 @@ class AutoencoderKLCogVideoX:
         # per-channel planes of this frame batch are strided inside pix: gather through a contiguous view
         src = pix[:, t0:t1].contiguous()
         L.pixels_to_cl(src, xin, T, H, W, 64)
-        x = self._causal_conv(self.enc_conv_in, xin, T, H, W, cache, "conv_in")
+        x, st = self._causal_conv(self.enc_conv_in, xin, T, H, W, cache, "conv_in", want_stats=True)
         del xin
         for bi, (res, down, compress_time) in enumerate(self.enc_down):
             for r in res:
-                x = self._resnet(r, x, T, H, W, None, cache)
+                x, st = self._resnet(r, x, T, H, W, None, cache, st)
             if down is not None:
                 C = down.cin
                 if compress_time:
@@ -238,11 +245,11 @@ class AutoencoderKLCogVideoX:
                 Ho, Wo = H // 2, W // 2
                 y = self._empty(T, Ho, Wo, C)
                 L.conv_cl(x, down.w, down.b, y, T, 1, 3, 3, 2, 0, Ho, Wo, down.cout)
-                x, H, W = y, Ho, Wo
+                x, H, W, st = y, Ho, Wo, False
         for r in self.enc_mid:
-            x = self._resnet(r, x, T, H, W, None, cache)
+            x, st = self._resnet(r, x, T, H, W, None, cache, st)
         C = self.enc_conv_out.cin
-        xin = self._norm_into_padded(self.enc_norm_out, x, T, H, W, C, None)
+        xin = self._norm_into_padded(self.enc_norm_out, x, T, H, W, C, None, fused_stats=st)
         return self._causal_conv(self.enc_conv_out, xin, T, H, W, cache, "conv_out"), (T, H, W)
 
     @staticmethod
@@ -351,13 +358,13 @@ class AutoencoderKLCogVideoX:
         xin = self._empty(T, h, w, 64)
         L.ncthw_to_cl(zsrc, xin, 16, T, h, w, 64, scale)
         zq = (xin, (T, h, w))                     # the (scaled) latent batch conditions every SpatialNorm3D
-        x = self._causal_conv(self.dec_conv_in, xin, T, h, w, cache, "conv_in")
+        x, st = self._causal_conv(self.dec_conv_in, xin, T, h, w, cache, "conv_in", want_stats=True)
         H, W = h, w
         for r in self.dec_mid:
-            x = self._resnet(r, x, T, H, W, zq, cache)
+            x, st = self._resnet(r, x, T, H, W, zq, cache, st)
         for (res, up, compress_time) in self.dec_up:
             for r in res:
-                x = self._resnet(r, x, T, H, W, zq, cache)
+                x, st = self._resnet(r, x, T, H, W, zq, cache, st)
             if up is not None:
                 C = up.cin
                 if compress_time and T > 1:
@@ -368,10 +375,10 @@ class AutoencoderKLCogVideoX:
                 L.upsample_nearest(x, y, T, H, W, C, compress_time)
                 x, T, H, W = y, To, 2 * H, 2 * W
                 y = self._empty(T, H, W, C)
-                L.conv_cl(x, up.w, up.b, y, T, 1, 3, 3, 1, 1, H, W, up.cout)
+                _, st = L.conv_cl(x, up.w, up.b, y, T, 1, 3, 3, 1, 1, H, W, up.cout, gn_partial=self._partial)
                 x = y
         C = self.dec_conv_out.cin
-        xin2 = self._norm_into_padded(self.dec_norm_out, x, T, H, W, C, zq)
+        xin2 = self._norm_into_padded(self.dec_norm_out, x, T, H, W, C, zq, fused_stats=st)
         del x
         # conv_out writes planar NCDHW straight into the output clip at frame offset f_off
         self._causal_conv(self.dec_conv_out, xin2, T, H, W, cache, "conv_out",

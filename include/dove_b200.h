@@ -112,10 +112,16 @@ int dove_velocity_bf16(const void* sample, const void* noise, void* out, int64_t
  *   stride: spatial stride (1 or 2); pad: low-side spatial zero pad (1 for "same" 3x3, 0 for the
  *   CogVideoXDownsample3D conv whose (0,1,0,1) pad is right/bottom only — high-side pad comes from TMA OOB fill).
  *   epilogue: DOVE_EPI_BIAS or DOVE_EPI_ADD (aux: [Tout,Ho,Wo,ld_aux]).
+ *   gn_partial / gn_done (both may be NULL): fused GroupNorm statistics of the OUTPUT tensor.  When the kernel chosen
+ *   for this shape supports it (the swapped-operand and CTA-pair kernels, i.e. all large convs), every CTA writes
+ *   per-group (sum, sum of squares) of the bf16-rounded outputs to gn_partial (dove_gn_partial_floats() floats,
+ *   zeroed by this call) and *gn_done (HOST int) is set to 1; the next GroupNorm then only needs dove_gn_finalize —
+ *   the separate statistics pass over the tensor disappears.  *gn_done = 0: run dove_gn_stats_bf16 as usual.
  * Replaces F.conv3d / F.conv2d in CogVideoXCausalConv3d, CogVideoXDownsample3D, CogVideoXUpsample3D. */
 int dove_conv_cl_bf16(const void* x, const void* w, const void* bias, void* y, int Tout, int Hin, int Win, int Cin,
                       int Cout_pad, int cout_valid, int64_t ldy, int kt, int kh, int kw, int stride, int pad,
-                      int Ho, int Wo, int epilogue, const void* aux, int64_t ld_aux, int out_mode, void* stream);
+                      int Ho, int Wo, int epilogue, const void* aux, int64_t ld_aux, int out_mode, float* gn_partial,
+                      int* gn_done, void* stream);
 
 /* Causal 3x3x3 convolution (CogVideoXCausalConv3d, stride 1, spatial zero pad 1) on the UN-padded frame batch
  * x [T,H,W,Cin] with ZERO-COPY temporal padding: the two frames preceding x are read from x_prev [2,H,W,Cin] (the
@@ -125,13 +131,16 @@ int dove_conv_cl_bf16(const void* x, const void* w, const void* bias, void* y, i
  * Other arguments as dove_conv_cl_bf16. */
 int dove_conv3d_causal_bf16(const void* x, const void* x_prev, const void* w, const void* bias, void* y, int T, int H,
                             int W, int Cin, int Cout_pad, int cout_valid, int64_t ldy, int epilogue, const void* aux,
-                            int64_t ld_aux, int out_mode, void* stream);
+                            int64_t ld_aux, int out_mode, float* gn_partial, int* gn_done, void* stream);
 
 /* GroupNorm statistics over a channels-last tensor [nvox, C]: mean/rstd per group -> stats[2*groups] fp32.
  * partial: workspace of dove_gn_partial_floats(nvox, groups) floats. */
 size_t dove_gn_partial_floats(int64_t nvox, int groups);
 int dove_gn_stats_bf16(const void* x, int64_t nvox, int C, int groups, float eps, float* partial, float* stats,
                        void* stream);
+
+/* mean / rstd per group from per-CTA partials written by a conv epilogue (see dove_conv_cl_bf16 gn_partial). */
+int dove_gn_finalize(const float* partial, int64_t nvox, int C, int groups, float eps, float* stats, void* stream);
 
 /* y = [silu]( bf16(bf16(GN(x))*cy + cb) ) or [silu](bf16(GN(x))) written to out (may be the frame-offset view of a
  * temporally padded conv input).  Spatial-norm variant (zq_y != NULL): cy/cb = conv_y/conv_b(zq) evaluated at
