@@ -92,3 +92,41 @@ def test_vae_shapes_small():
         assert m.parameters.shape == (1, 32, 3, 2, 2)
         out = vae.decode(m.mode()).sample
     assert out.shape == (1, 3, 9, 16, 16) and torch.isfinite(out).all()
+
+
+def test_frame_bookkeeping_against_oracle_control_flow():
+    """The product's frame-count bookkeeping (latent_frames, decoded frame counts, tile integers) against the oracle's
+    actual encode/decode control flow, evaluated shape-only on the meta device."""
+    from dove_b200.vae import AutoencoderKLCogVideoX as P
+    with torch.device("meta"):
+        vae = OracleAutoencoderKLCogVideoX()
+        for F in (8, 9, 17, 24, 25, 33, 54):
+            m = vae._encode(torch.empty(1, 3, F, 32, 48))
+            assert m.shape == (1, 32, P.latent_frames(F), 4, 6), F
+            d = vae._decode(torch.empty(1, 16, m.shape[2], 4, 6))
+            # decoded frame count: first latent batch keeps frame 0 single (odd) -> what the product pre-computes
+            total = 0
+            for s, e in P.frame_batches(m.shape[2], 2):
+                t = e - s
+                for _ in range(2):
+                    t = (1 + 2 * (t - 1) if t % 2 else 2 * t) if t > 1 else t
+                total += t
+            assert d.shape == (1, 3, total, 32, 48), (F, d.shape, total)
+    p = P.__new__(P)
+    from types import SimpleNamespace
+    from dove_b200.weights import VAE_CONFIG
+    p.config = SimpleNamespace(**VAE_CONFIG)
+    enc, dec = p.tile_ints()
+    assert (enc["stride_h"], enc["stride_w"], enc["blend_h"], enc["blend_w"], enc["limit_h"], enc["limit_w"]) == \
+        (200, 288, 5, 9, 25, 36)
+    assert (dec["stride_h"], dec["stride_w"], dec["blend_h"], dec["blend_w"], dec["limit_h"], dec["limit_w"]) == \
+        (25, 36, 40, 72, 200, 288)
+
+
+def test_oracle_blend_ramp():
+    a = torch.ones(1, 1, 1, 6, 4)
+    b = torch.zeros(1, 1, 1, 6, 4)
+    out = OracleAutoencoderKLCogVideoX.blend_v(a, b.clone(), 4)
+    assert torch.allclose(out[0, 0, 0, :, 0], torch.tensor([1.0, 0.75, 0.5, 0.25, 0.0, 0.0]))
+    out = OracleAutoencoderKLCogVideoX.blend_h(a, b.clone(), 2)
+    assert torch.allclose(out[0, 0, 0, 0], torch.tensor([1.0, 0.5, 0.0, 0.0]))
