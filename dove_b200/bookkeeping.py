@@ -79,9 +79,28 @@ def enumerate_units(video_shape, chunk_len, overlap_t, tile_size_hw, overlap_hw)
             for t in make_spatial_tiles(H, W, tile_size_hw, overlap_hw)]
 
 
-def partition_units(units, world_size):
-    """Static round-robin assignment of units to ranks: rank r owns units r, r+W, ..."""
-    return [list(range(r, len(units), world_size)) for r in range(world_size)]
+def unit_cost(unit):
+    """Work proxy of a unit: voxels (frames x rows x cols).  The VAE cost is linear in it; attention adds a mildly
+    super-linear term, so bigger units are placed first."""
+    (t0, t1), (h0, h1, w0, w1) = unit
+    return (t1 - t0) * (h1 - h0) * (w1 - w0)
+
+
+def partition_units(units, world_size, balance=True):
+    """Static assignment of units to ranks.  balance=True: longest-processing-time-first greedy
+    (units sorted by cost, ties by index, each given to the least-loaded rank, ties by rank) — e.g. the 8 cfg-3 tiles
+    (6 of 416x352 + 2 of 416x416) on 2 or 4 ranks get one wide tile per rank instead of both on the last rank.
+    balance=False: plain round-robin (rank r owns units r, r+W, ...).  Deterministic: every rank computes the same map."""
+    if not balance:
+        return [list(range(r, len(units), world_size)) for r in range(world_size)]
+    order = sorted(range(len(units)), key=lambda k: (-unit_cost(units[k]), k))
+    loads = [0] * world_size
+    parts = [[] for _ in range(world_size)]
+    for k in order:
+        r = min(range(world_size), key=lambda i: (loads[i], i))
+        parts[r].append(k)
+        loads[r] += unit_cost(units[k])
+    return [sorted(p) for p in parts]
 
 
 def frame_padding(F):

@@ -5,7 +5,7 @@ units = chunks x tiles in loop order; each unit is super-resolved independently;
 (half the overlap trimmed on interior sides, no blending) is written; every output voxel must be written exactly
 once or the run aborts.  B200-first differences: the stitched output stays in HBM (one D2H at the end instead of
 one synchronous D2H per unit, ref :712-717), and with world_size > 1 the units are statically partitioned
-round-robin over ranks (no data-path collective while computing) followed by ONE all-gather of the packed valid
+(cost-balanced, deterministic) over ranks (no data-path collective while computing) followed by ONE all-gather of the packed valid
 regions — NCCL over NVLink on GPUs, gloo in the CPU tests of this host logic.
 
 RNG: the reference draws each unit's latent noise from the global generator in loop order (seed 42 once,

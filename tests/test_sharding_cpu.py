@@ -64,7 +64,15 @@ def test_partition_covers_all_units_once():
     shape = (1, 3, 33, 768, 1280)
     units = enumerate_units(shape, 0, 8, (416, 352), (64, 64))
     assert len(units) == 8                                   # exactly 8 spatial tiles for cfg-3
+    from dove_b200.bookkeeping import unit_cost
     for world in (1, 2, 4, 8, 3):
-        parts = partition_units(units, world)
-        assert sorted(k for p in parts for k in p) == list(range(len(units)))
-        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+        for balance in (True, False):
+            parts = partition_units(units, world, balance=balance)
+            assert sorted(k for p in parts for k in p) == list(range(len(units)))
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+    # the two 416-wide tiles (indices 3 and 7) must not land on the same rank when balancing over 2 or 4 ranks
+    for world in (2, 4):
+        loads = [sum(unit_cost(units[k]) for k in p) for p in partition_units(units, world)]
+        rr = [sum(unit_cost(units[k]) for k in p) for p in partition_units(units, world, balance=False)]
+        assert max(loads) < max(rr)
+        assert all(not ({3, 7} <= set(p)) for p in partition_units(units, world))
