@@ -18,6 +18,7 @@ _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "libdove_b200.so"
 
 EPI_BIAS, EPI_GELU_TANH, EPI_GATED_RES, EPI_ADD = 0, 1, 2, 3
+DEFAULT_ATTN_VARIANT = 3      # must match g_attn_variant in csrc/attn.cu (v3 kernel, 2/8 of the exps on the FMA pipe)
 
 
 class DoveError(RuntimeError):
@@ -52,7 +53,6 @@ _SIGS = {
     "dove_gn_stats_bf16": (c_int, [c_void_p, c_int64, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     "dove_gn_apply_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
-    "dove_causal_pad_frames": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
     "dove_time_pool_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p]),
     "dove_upsample_nearest_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "dove_pixels_to_cl_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
@@ -199,7 +199,7 @@ def velocity(sample, noise, out, a, b):
 
 
 # ---------------------------------------------------------------------------------------------- VAE ops
-_gn_done = ctypes.c_int(0)
+OUT_CL, OUT_PLANAR, OUT_PLANAR_POST, OUT_PLANAR_U8 = 0, 1, 2, 3
 
 
 def conv_cl(x, w, bias, y, Tout, kt, kh, kw, stride, pad, Ho, Wo, cout_valid, epilogue=EPI_BIAS, aux=None,
@@ -209,26 +209,30 @@ def conv_cl(x, w, bias, y, Tout, kt, kh, kw, stride, pad, Ho, Wo, cout_valid, ep
     assert Tin == Tout + kt - 1, (Tin, Tout, kt)
     Cout_pad = w.shape[0]
     ldy = y.shape[-1] if out_mode == 0 else (plane_stride or Tout * Ho * Wo)
-    assert x.dtype == torch.bfloat16 and x.is_contiguous() and y.dtype == torch.bfloat16
+    assert x.dtype == torch.bfloat16 and x.is_contiguous()
+    assert y.dtype == (torch.uint8 if out_mode == OUT_PLANAR_U8 else torch.bfloat16)
+    gn_done = ctypes.c_int(0)          # per call: the C entry point writes it before returning
     _call("dove_conv_cl_bf16", _p(x), _p(_bf16c(w)), _p(bias), _p(y), Tout, Hin, Win, Cin, Cout_pad,
           cout_valid, ldy, kt, kh, kw, stride, pad, Ho, Wo, epilogue, _p(aux),
           aux.shape[-1] if aux is not None else 0, out_mode, _p(gn_partial),
-          ctypes.byref(_gn_done) if gn_partial is not None else None, _stream())
-    return (y, bool(_gn_done.value)) if gn_partial is not None else y
+          ctypes.byref(gn_done) if gn_partial is not None else None, _stream())
+    return (y, bool(gn_done.value)) if gn_partial is not None else y
 
 
 def conv3d_causal(x, x_prev, w, bias, y, cout_valid, epilogue=EPI_BIAS, aux=None, out_mode=0, plane_stride=0,
                   gn_partial=None):
     """Causal 3x3x3 conv on the un-padded frame batch x [T,H,W,Cin]; x_prev [2,H,W,Cin] (cache view) or None."""
     T, H, W, Cin = x.shape
-    assert x.dtype == torch.bfloat16 and x.is_contiguous() and y.dtype == torch.bfloat16
+    assert x.dtype == torch.bfloat16 and x.is_contiguous()
+    assert y.dtype == (torch.uint8 if out_mode == OUT_PLANAR_U8 else torch.bfloat16)
     if x_prev is not None:
         assert x_prev.shape == (2, H, W, Cin) and x_prev.is_contiguous() and x_prev.dtype == torch.bfloat16
     ldy = y.shape[-1] if out_mode == 0 else (plane_stride or T * H * W)
+    gn_done = ctypes.c_int(0)
     _call("dove_conv3d_causal_bf16", _p(x), _p(x_prev), _p(_bf16c(w)), _p(bias), _p(y), T, H, W, Cin, w.shape[0],
           cout_valid, ldy, epilogue, _p(aux), aux.shape[-1] if aux is not None else 0, out_mode, _p(gn_partial),
-          ctypes.byref(_gn_done) if gn_partial is not None else None, _stream())
-    return (y, bool(_gn_done.value)) if gn_partial is not None else y
+          ctypes.byref(gn_done) if gn_partial is not None else None, _stream())
+    return (y, bool(gn_done.value)) if gn_partial is not None else y
 
 
 def gn_finalize(partial, nvox, C, groups, eps, stats):
@@ -253,10 +257,6 @@ def gn_apply(x, out, T, H, W, C, groups, stats, gamma, beta, silu, zq_y=None, zq
     _call("dove_gn_apply_bf16", _p(x), _p(out), T, H, W, C, groups, _p(stats), _p(gamma), _p(beta), int(silu),
           _p(zq_y), _p(zq_b), Tz, hz, wz, _stream())
     return out
-
-
-def causal_pad_frames(xin, T, frame_elems, cache, new_cache):
-    _call("dove_causal_pad_frames", _p(xin), T, frame_elems, _p(cache), _p(new_cache), _stream())
 
 
 def time_pool(x, y, T, frame_elems):

@@ -14,6 +14,9 @@
 // the rare tiles where that happens (P stays <= 2^8, well inside bf16/fp32 range); the final 1/l normalisation
 // uses the same stale max, so the result is exact softmax.
 // TMEM columns: S = 0..127, O = 128..191, P = 192..255 (bf16 pairs).
+#include <atomic>
+#include <mutex>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -57,7 +60,7 @@ __device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
 }
 
 __global__ void __launch_bounds__(192, 2)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
+attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -260,6 +263,364 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
   }
 }
 
+// =====================================================================================================================
+// v3: ONE CTA PER SM, TWO 128-row query tiles per CTA (256 query rows) that share every staged K/V tile, so the
+// L2 -> SM traffic per query row is half of v2's, and a leaner softmax:
+//   * no row-max pass in the steady state: the exponent reference m_used is kept from earlier tiles and the
+//     probabilities are computed directly; the row sum of the tile detects the (rare) case where a score exceeded
+//     m_used by more than 8 log2 units (p > 2^8) and only then the exact path (max, rescale of O in TMEM) is run.
+//     The first KV tile and a ragged last tile always take the exact path.
+//   * the MUFU unit (16 ex2/clk/SM) bounds a head_dim-64 attention at 50 % tensor pipe, so EMU8/8 of the exponentials
+//     are evaluated on the FMA pipe instead (Cody-Waite split with the 1.5*2^23 magic add + a degree-3 minimax
+//     polynomial on [-0.5, 0.5], relative error 7.5e-5 << the bf16 rounding of P; exponent merged with one
+//     integer shift-add), all in packed f32x2 FMAs.
+//   warp 0 TMA producer (Q0, Q1 once; 3-stage ring of K/V tiles), warp 1 TMEM owner + MMA issuer,
+//   warps 2..5 softmax of query tile 0, warps 6..9 softmax of query tile 1 (one row per thread).
+// TMEM (512 columns): tile t at base + 256 t:  S = +0..127 (fp32), O = +128..191 (fp32), P = +192..255 (bf16 pairs).
+constexpr int A3_STAGES = 3;
+constexpr size_t A3_SMEM = 1024 + ATT_TILE_BYTES * (2 + 2 * A3_STAGES) + 256;
+constexpr float A3_OVERFLOW = 256.0f;   // 2^ATT_LAZY_THRESHOLD
+
+__host__ __device__ constexpr bool a3_emu_pair(int i, int emu8) { return ((i * emu8) % 8) < emu8 && emu8 > 0; }
+
+// 2^x on the FMA pipe, two lanes at a time.  x below -126 is clamped (result ~ 0, exact enough: such a key has weight
+// < 2^-126); x above 127 would wrap the exponent field SILENTLY, so the largest magic-shifted argument seen is
+// tracked in tmax (one 3-input max per pair) and the caller reruns the tile on the exact path when it exceeds 127.
+__device__ __forceinline__ void ex2_emu_x2(uint64_t x2, float& p0, float& p1, float& tmax) {
+  float x0, x1;
+  unpack_f32x2(x2, x0, x1);
+  x0 = fmaxf(x0, -126.0f);
+  x1 = fmaxf(x1, -126.0f);
+  const uint64_t xc = pack_f32x2(x0, x1);
+  const uint64_t magic = pack_f32x2(12582912.0f, 12582912.0f);          // 1.5 * 2^23: low mantissa bits = round(x)
+  const uint64_t nmagic = pack_f32x2(-12582912.0f, -12582912.0f);
+  const uint64_t t2 = add_f32x2(xc, magic);
+  const uint64_t n2 = add_f32x2(t2, nmagic);                            // round(x) as a float
+  const uint64_t r2 = fma_f32x2(n2, pack_f32x2(-1.0f, -1.0f), xc);      // r = x - round(x) in [-0.5, 0.5]
+  uint64_t q2 = fma_f32x2(pack_f32x2(0.05517132207751274f, 0.05517132207751274f), r2,
+                          pack_f32x2(0.24261054396629333f, 0.24261054396629333f));
+  q2 = fma_f32x2(q2, r2, pack_f32x2(0.6932609677314758f, 0.6932609677314758f));
+  q2 = fma_f32x2(q2, r2, pack_f32x2(0.9999281167984009f, 0.9999281167984009f));
+  float q0, q1, t0, t1;
+  unpack_f32x2(q2, q0, q1);
+  unpack_f32x2(t2, t0, t1);
+  tmax = fmaxf(tmax, fmaxf(t0, t1));
+  p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));
+  p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
+}
+
+template <int EMU8>
+__global__ void __launch_bounds__(320, 1)
+attn_fwd_v3_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                   // 2 query tiles
+  uint8_t* sK = sQ + 2 * ATT_TILE_BYTES;
+  uint8_t* sV = sK + A3_STAGES * ATT_TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + A3_STAGES * ATT_TILE_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;
+  uint64_t* kv_empty = kv_full + A3_STAGES;
+  uint64_t* s_full = kv_empty + A3_STAGES;              // [2]
+  uint64_t* p_full = s_full + 2;                        // [2]
+  uint64_t* pv_done = p_full + 2;                       // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pv_done + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.y;
+  const int q0 = blockIdx.x * 256;
+  const int qcol = head * 64, kcol = (p.heads + head) * 64, vcol = (2 * p.heads + head) * 64;
+  const int nkv = p.nkv;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < A3_STAGES; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&p_full[t], 4);
+      mbar_init(&pv_done[t], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    mbar_expect_tx(q_full, 2 * ATT_TILE_BYTES);
+    tma_load_2d(sQ, &tm, q_full, qcol, q0);
+    tma_load_2d(sQ + ATT_TILE_BYTES, &tm, q_full, qcol, q0 + 128);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait(&kv_empty[stage], phase ^ 1);
+      mbar_expect_tx(&kv_full[stage], 2 * ATT_TILE_BYTES);
+      tma_load_2d(sK + stage * ATT_TILE_BYTES, &tm, &kv_full[stage], kcol, j * 128);
+      tma_load_2d(sV + stage * ATT_TILE_BYTES, &tm, &kv_full[stage], vcol, j * 128);
+      if (++stage == A3_STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // Q (K-major) x K (K-major)
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);    // P (TMEM) x V (MN-major)
+    auto issue_s = [&](int t, int stage) {
+      const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ + t * ATT_TILE_BYTES));
+      const uint64_t kdesc = umma_desc_sw128(smem_u32(sK + stage * ATT_TILE_BYTES));
+      const uint32_t TS = tmem_base + t * 256;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_ss(TS, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+      umma_commit(&s_full[t]);
+    };
+    mbar_wait(q_full, 0);
+    mbar_wait(&kv_full[0], 0);
+    tc_fence_after();
+    issue_s(0, 0);
+    issue_s(1, 0);
+    int stage = 0, nstage = 1;
+    uint32_t nphase = 0;                      // parity of kv_full[nstage] for tile j + 1
+    for (int j = 0; j < nkv; ++j) {
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        mbar_wait(&p_full[t], j & 1);        // softmax_t(j) has read all of S_t(j) and written P_t(j)
+        tc_fence_after();
+        if (j + 1 < nkv) {                   // S_t(j+1) first: softmax_t(j+1) can start while PV_t(j) runs
+          if (t == 0) {
+            mbar_wait(&kv_full[nstage], nphase);
+            tc_fence_after();
+          }
+          issue_s(t, nstage);
+        }
+        const uint64_t vdesc = umma_desc_sw128(smem_u32(sV + stage * ATT_TILE_BYTES));
+        const uint32_t TO = tmem_base + t * 256 + 128, TP = tmem_base + t * 256 + 192;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // K = 128 keys, 16 per instruction: P +8 TMEM columns, V +16 rows = 2048 B
+          umma_ts(TO, TP + k * 8, vdesc + 128 * k, idesc_o, (j | k) != 0);
+        umma_commit(&pv_done[t]);
+      }
+      umma_commit(&kv_empty[stage]);          // both tiles are done with K_j and V_j once everything above retires
+      stage = nstage;
+      if (++nstage == A3_STAGES) {
+        nstage = 0;
+        nphase ^= 1;
+      }
+    }
+  } else if (warp >= 2) {
+    // ===================== softmax =====================
+    const int t = (warp - 2) >> 2;          // query tile of this warpgroup
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;            // query row in tile == TMEM lane
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t TS = tmem_base + t * 256 + lane_off, TO = TS + 128, TP = TS + 192;
+    float m_used = -INFINITY, l_run = 0.f;
+    const float sl2 = p.scale_log2;
+    const uint64_t sl2_2 = pack_f32x2(sl2, sl2);
+    const bool ragged = (nkv * 128 != p.rows);
+
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait(&s_full[t], j & 1);
+      tc_fence_after();
+      bool exact = (j == 0) || (ragged && j == nkv - 1);
+      bool waited_pv = (j == 0);            // P_t / O_t are only touched after PV_t(j-1) has retired
+      float lsum = 0.f;
+      if (!exact) {
+        // ---------- steady state: probabilities straight from the stale reference max ----------
+        const float neg_m = -m_used;
+        const uint64_t negm_2 = pack_f32x2(neg_m, neg_m);
+        uint64_t lsA = 0ull, lsB = 0ull;
+        float tmax = 0.f;
+        uint32_t vbuf[2][32];                  // TMEM loads run one 32-column chunk ahead of the arithmetic
+        tmem_ld32(TS, vbuf[0]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t* v = vbuf[c & 1];
+          tmem_ld_wait();
+          if (c < 3) tmem_ld32(TS + (c + 1) * 32, vbuf[(c + 1) & 1]);
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const uint64_t x2 = fma_f32x2(pack_f32x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), sl2_2,
+                                          negm_2);
+            float p0, p1;
+            if (a3_emu_pair(i, EMU8)) {
+              ex2_emu_x2(x2, p0, p1, tmax);
+            } else {
+              float x0, x1;
+              unpack_f32x2(x2, x0, x1);
+              p0 = ex2_approx(x0);
+              p1 = ex2_approx(x1);
+            }
+            if (i & 1) lsB = add_f32x2(lsB, pack_f32x2(p0, p1));
+            else lsA = add_f32x2(lsA, pack_f32x2(p0, p1));
+            pk[i] = pack_bf16x2(p0, p1);
+          }
+          if (!waited_pv) {
+            mbar_wait(&pv_done[t], (j - 1) & 1);
+            tc_fence_after();
+            waited_pv = true;
+          }
+          tmem_st16(TP + c * 16, pk);
+        }
+        float a0, a1, b0, b1;
+        unpack_f32x2(lsA, a0, a1);
+        unpack_f32x2(lsB, b0, b1);
+        lsum = (a0 + a1) + (b0 + b1);
+        // a score more than 8 log2 units above m_used (or a NaN) shows up in the row sum: redo this tile exactly
+        exact = __any_sync(0xffffffffu, !(lsum <= A3_OVERFLOW) || tmax > 12582912.0f + 127.0f);
+      }
+      float alpha = 1.0f;
+      if (exact) {
+        // ---------- exact path: row max, lazy rescale of O, masked tail (first / last / overflowing tiles) ----------
+        const int kbase = j * 128;
+        const bool tail = kbase + 128 > p.rows;
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld32(TS + c * 32, v);
+          tmem_ld_wait();
+          if (tail) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (kbase + c * 32 + i >= p.rows) v[i] = 0xff800000u;   // -inf
+          }
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              m4[u] = fmaxf(m4[u], fmaxf(__uint_as_float(v[i + 2 * u]), __uint_as_float(v[i + 2 * u + 1])));
+          }
+          mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+        }
+        const float m_new = fmaxf(m_used, mx * sl2);
+        const bool need = (m_new - m_used) > ATT_LAZY_THRESHOLD;     // first tile: inf > 8
+        const bool warp_need = __any_sync(0xffffffffu, need);
+        if (need) {
+          alpha = ex2_approx(m_used - m_new);
+          m_used = m_new;
+        }
+        if (!waited_pv) {
+          mbar_wait(&pv_done[t], (j - 1) & 1);
+          tc_fence_after();
+          waited_pv = true;
+        }
+        if (j > 0 && warp_need) {            // O *= alpha (TMEM read-modify-write; rare after the first tiles)
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t o[32];
+            tmem_ld32(TO + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(TO + c * 32, o);
+          }
+        }
+        const float neg_m = -m_used;
+        const uint64_t negm_2 = pack_f32x2(neg_m, neg_m);
+        uint64_t lsA = 0ull, lsB = 0ull;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld32(TS + c * 32, v);
+          tmem_ld_wait();
+          if (tail) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (kbase + c * 32 + i >= p.rows) v[i] = 0xff800000u;
+          }
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const uint64_t x2 = fma_f32x2(pack_f32x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), sl2_2,
+                                          negm_2);
+            float x0, x1;
+            unpack_f32x2(x2, x0, x1);
+            const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+            if (i & 1) lsB = add_f32x2(lsB, pack_f32x2(p0, p1));
+            else lsA = add_f32x2(lsA, pack_f32x2(p0, p1));
+            pk[i] = pack_bf16x2(p0, p1);
+          }
+          tmem_st16(TP + c * 16, pk);
+        }
+        float a0, a1, b0, b1;
+        unpack_f32x2(lsA, a0, a1);
+        unpack_f32x2(lsB, b0, b1);
+        lsum = (a0 + a1) + (b0 + b1);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[t]);
+      l_run = l_run * alpha + lsum;
+    }
+    mbar_wait(&pv_done[t], (nkv - 1) & 1);
+    tc_fence_after();
+    const int row = q0 + t * 128 + r;
+    const float inv = 1.0f / l_run;
+    uint4* op = reinterpret_cast<uint4*>(p.out + static_cast<long long>(row) * (p.heads * 64) + head * 64);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t o[32];
+      tmem_ld32(TO + c * 32, o);
+      tmem_ld_wait();
+      if (row < p.rows) {
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(o[jj * 8 + 0]) * inv, __uint_as_float(o[jj * 8 + 1]) * inv);
+          w.y = pack_bf16x2(__uint_as_float(o[jj * 8 + 2]) * inv, __uint_as_float(o[jj * 8 + 3]) * inv);
+          w.z = pack_bf16x2(__uint_as_float(o[jj * 8 + 4]) * inv, __uint_as_float(o[jj * 8 + 5]) * inv);
+          w.w = pack_bf16x2(__uint_as_float(o[jj * 8 + 6]) * inv, __uint_as_float(o[jj * 8 + 7]) * inv);
+          op[c * 4 + jj] = w;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// variant: 0 = v2 (2 CTAs/SM, one query tile each); 1 + e = v3 with e/8 of the exponentials on the FMA pipe
+static std::atomic<int> g_attn_variant{3};
+int set_attn_variant(int v) {
+  if (v < 0 || v > 6) return set_error(DOVE_E_BAD_ARG, "attn_variant must be 0..6");
+  g_attn_variant.store(v);
+  return DOVE_OK;
+}
+
+template <typename K>
+static int set_smem_once(K kernel, size_t bytes, std::once_flag& flag) {
+  cudaError_t err = cudaSuccess;
+  std::call_once(flag, [&] {
+    err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+  });
+  return err == cudaSuccess ? DOVE_OK : check_cuda(err, "cudaFuncSetAttribute(attention)");
+}
+
+template <int EMU8>
+static int launch_v3(const CUtensorMap& tm, const AttnParams& p, cudaStream_t st) {
+  static std::once_flag flag;
+  if (int e = set_smem_once(attn_fwd_v3_kernel<EMU8>, A3_SMEM, flag)) return e;
+  dim3 grid((p.rows + 255) / 256, p.heads);
+  attn_fwd_v3_kernel<EMU8><<<grid, 320, A3_SMEM, st>>>(tm, p);
+  DOVE_LAUNCH_CHECK("attn_fwd_v3_kernel");
+  return DOVE_OK;
+}
+
 static int attention_launch(const void* qkv, void* out, int rows, int heads, float scale, cudaStream_t st) {
   if (int e = ensure_init()) return e;
   DOVE_CHECK_ARG(rows > 0 && heads > 0, "attention: empty problem");
@@ -276,16 +637,21 @@ static int attention_launch(const void* qkv, void* out, int rows, int heads, flo
   p.nkv = (rows + 127) / 128;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.out = static_cast<bf16*>(out);
-  dim3 grid((rows + 127) / 128, heads);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(ATT_SMEM));
-    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(attn)");
-    attr_set = true;
+  const int variant = g_attn_variant.load();
+  switch (variant) {
+    case 1: return launch_v3<0>(tm, p, st);
+    case 2: return launch_v3<1>(tm, p, st);
+    case 3: return launch_v3<2>(tm, p, st);
+    case 4: return launch_v3<3>(tm, p, st);
+    case 5: return launch_v3<4>(tm, p, st);
+    case 6: return launch_v3<5>(tm, p, st);
+    default: break;
   }
-  attn_fwd_kernel<<<grid, 192, ATT_SMEM, st>>>(tm, p);
-  DOVE_LAUNCH_CHECK("attn_fwd_kernel");
+  static std::once_flag flag;
+  if (int e = set_smem_once(attn_fwd_v2_kernel, ATT_SMEM, flag)) return e;
+  dim3 grid((rows + 127) / 128, heads);
+  attn_fwd_v2_kernel<<<grid, 192, ATT_SMEM, st>>>(tm, p);
+  DOVE_LAUNCH_CHECK("attn_fwd_v2_kernel");
   return DOVE_OK;
 }
 

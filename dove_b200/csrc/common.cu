@@ -31,6 +31,7 @@ int num_sms() { return g_num_sms; }
 
 static int g_opt_conv2cta = 1;
 int get_option_conv2cta() { return g_opt_conv2cta; }
+int set_attn_variant(int v);
 
 int ensure_init() {
   if (g_device < 0) return set_error(DOVE_E_NOT_INIT, "dove_init(device) has not been called");
@@ -69,6 +70,7 @@ extern "C" int dove_set_option(const char* name, int value) {
     g_opt_conv2cta = value;
     return DOVE_OK;
   }
+  if (name && !strcmp(name, "attn_variant")) return set_attn_variant(value);
   return set_error(DOVE_E_BAD_ARG, "unknown option %s", name ? name : "(null)");
 }
 

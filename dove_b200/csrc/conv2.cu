@@ -16,6 +16,8 @@
 // warps 2..9 epilogue (both CTAs, each on its own 128 accumulator lanes).  Separate A and B mbarrier rings; all
 // "full" barriers live in the leader CTA (both CTAs' TMA bytes are credited there), "empty" barriers are released
 // in both CTAs by multicast tcgen05.commit.
+#include <mutex>
+
 #include "gemm_common.cuh"
 
 namespace dove {
@@ -214,13 +216,11 @@ template <int BN>
 static int launch_conv2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmP, const GemmParams& p,
                         int kt, cudaStream_t st) {
   using Cfg = Conv2Cfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv2cta_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(Cfg::SMEM));
-    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(conv2cta_kernel)");
-    attr_set = true;
-  }
+  static std::once_flag attr_once;   // thread-safe one-time opt-in to > 48 KB dynamic shared memory
+  cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [&] { attr_err = cudaFuncSetAttribute(conv2cta_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(Cfg::SMEM)); });
+  if (attr_err != cudaSuccess) return check_cuda(attr_err, "cudaFuncSetAttribute(conv2cta_kernel)");
   const int total = p.num_m_tiles * p.num_n_tiles;
   const int max_pairs = num_sms() / 2;
   const int pairs = total < max_pairs ? total : max_pairs;

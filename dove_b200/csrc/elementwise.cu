@@ -11,6 +11,15 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// SiLU with ONE MUFU op per element (x * sigmoid(x) = h + h * tanh(h), h = x/2) instead of ex2 + rcp: the GroupNorm-apply
+// pass was MUFU-bound at ~0.5 of HBM speed with two.  tanh.approx.f32 is accurate to ~2^-11 of tanh, i.e. an absolute
+// error <= |x| * 2.5e-4 in the result, far below the bf16 rounding of the stored output (2^-9 relative).
+__device__ __forceinline__ float silu_fast(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
   float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
   f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
@@ -340,7 +349,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
         }
         if (apply_silu) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) f[k] = silu_f(f[k]);
+          for (int k = 0; k < 8; ++k) f[k] = silu_fast(f[k]);
         }
         *reinterpret_cast<uint4*>(orow + static_cast<long long>(xx) * C) = pack8(f);
       }
@@ -651,30 +660,6 @@ extern "C" int dove_gn_apply_bf16(const void* x, void* out, int T, int H, int W,
       static_cast<const bf16*>(beta), apply_silu, static_cast<const bf16*>(zq_y), static_cast<const bf16*>(zq_b), Tz, hz,
       wz, x_shift);
   DOVE_LAUNCH_CHECK("gn_apply_kernel");
-  return DOVE_OK;
-}
-
-extern "C" int dove_causal_pad_frames(void* xin, int T, int64_t frame_elems, const void* cache, void* new_cache,
-                                      void* stream) {
-  if (int e = ensure_init()) return e;
-  DOVE_CHECK_ARG(T >= 1 && frame_elems > 0, "causal_pad: bad shape");
-  bf16* p = static_cast<bf16*>(xin);
-  const size_t fb = static_cast<size_t>(frame_elems) * 2;
-  cudaError_t e;
-  if (cache) {
-    e = cudaMemcpyAsync(p, cache, 2 * fb, cudaMemcpyDeviceToDevice, ST(stream));
-    if (e != cudaSuccess) return check_cuda(e, "causal_pad copy cache");
-  } else {
-    for (int i = 0; i < 2; ++i) {
-      e = cudaMemcpyAsync(p + i * frame_elems, p + 2 * frame_elems, fb, cudaMemcpyDeviceToDevice, ST(stream));
-      if (e != cudaSuccess) return check_cuda(e, "causal_pad replicate");
-    }
-  }
-  if (new_cache) {
-    e = cudaMemcpyAsync(new_cache, p + static_cast<long long>(T) * frame_elems, 2 * fb, cudaMemcpyDeviceToDevice,
-                        ST(stream));
-    if (e != cudaSuccess) return check_cuda(e, "causal_pad save cache");
-  }
   return DOVE_OK;
 }
 

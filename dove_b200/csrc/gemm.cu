@@ -9,6 +9,8 @@
 // warps 2..9 = epilogue (TMEM -> registers -> fused epilogue -> global; two warps per TMEM lane quarter, each
 // taking every other 32-column chunk, so the epilogue has 2 warps per SMSP to hide its own latencies).  Accumulators are double-buffered in
 // TMEM (2 x BN fp32 columns) so the epilogue of tile i overlaps the main loop of tile i+1.
+#include <mutex>
+
 #include "gemm_common.cuh"
 
 namespace dove {
@@ -276,13 +278,11 @@ template <int BN, bool kConv>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmP, const GemmParams& p,
                        cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
-  static bool attr_set = false;   // idempotent; benign race
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(umma_gemm_kernel<BN, kConv>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(Cfg::SMEM));
-    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(umma_gemm_kernel)");
-    attr_set = true;
-  }
+  static std::once_flag attr_once;   // thread-safe one-time opt-in to > 48 KB dynamic shared memory
+  cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [&] { attr_err = cudaFuncSetAttribute(umma_gemm_kernel<BN, kConv>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(Cfg::SMEM)); });
+  if (attr_err != cudaSuccess) return check_cuda(attr_err, "cudaFuncSetAttribute(umma_gemm_kernel)");
   const int total = p.num_m_tiles * p.num_n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
   umma_gemm_kernel<BN, kConv><<<grid, 320, Cfg::SMEM, st>>>(tmA, tmB, tmP, p);
@@ -293,13 +293,11 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
 static int launch_conv_trans(const CUtensorMap& tmX, const CUtensorMap& tmW, const CUtensorMap& tmP, const GemmParams& p,
                              cudaStream_t st) {
   using Cfg = GemmCfg<256>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(umma_gemm_kernel<256, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(Cfg::SMEM));
-    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(umma_gemm_kernel trans)");
-    attr_set = true;
-  }
+  static std::once_flag attr_once;   // thread-safe one-time opt-in to > 48 KB dynamic shared memory
+  cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [&] { attr_err = cudaFuncSetAttribute(umma_gemm_kernel<256, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(Cfg::SMEM)); });
+  if (attr_err != cudaSuccess) return check_cuda(attr_err, "cudaFuncSetAttribute(umma_gemm_kernel trans)");
   const int total = p.num_m_tiles * p.num_n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
   umma_gemm_kernel<256, true, true><<<grid, 320, Cfg::SMEM, st>>>(tmX, tmW, tmP, p);
@@ -405,9 +403,9 @@ static int conv_impl(const void* x, const void* x_prev, int cached, const void* 
   DOVE_CHECK_ARG(Cout_pad % 16 == 0 && cout_valid <= Cout_pad, "conv: Cout_pad=%d must be a multiple of 16", Cout_pad);
   DOVE_CHECK_ARG(stride == 1 || stride == 2, "conv: stride must be 1 or 2");
   DOVE_CHECK_ARG(epilogue == DOVE_EPI_BIAS || epilogue == DOVE_EPI_ADD, "conv: epilogue must be BIAS or ADD");
-  DOVE_CHECK_ARG(out_mode == 0 || out_mode == 1, "conv: bad out_mode");
+  DOVE_CHECK_ARG(out_mode >= 0 && out_mode <= 3, "conv: bad out_mode");
   if (out_mode == 0) DOVE_CHECK_ARG(ldy % 8 == 0, "conv: ldy must be a multiple of 8");
-  if (out_mode == 1) DOVE_CHECK_ARG(ldy >= static_cast<long long>(Tout) * Ho * Wo, "conv: planar plane stride too small");
+  if (out_mode >= 1) DOVE_CHECK_ARG(ldy >= static_cast<long long>(Tout) * Ho * Wo, "conv: planar plane stride too small");
   if (epilogue == DOVE_EPI_ADD) DOVE_CHECK_ARG(aux && ld_aux % 8 == 0, "conv: add epilogue needs aux");
   {   // CTA-pair kernel with in-smem reuse of the W taps for the big stride-1 3x3(x3) convs on wide images
     const int opt = get_option_conv2cta();
@@ -588,7 +586,7 @@ static int conv_impl(const void* x, const void* x_prev, int cached, const void* 
   p.ld_aux = ld_aux;
   p.n_valid = cout_valid;
   p.out_mode = out_mode;
-  p.rows_total = out_mode == 1 ? ldy : static_cast<long long>(Tout) * Ho * Wo;
+  p.rows_total = out_mode >= 1 ? ldy : static_cast<long long>(Tout) * Ho * Wo;
   return dispatch_bn<true>(bn, tmA, tmB, tmP, p, static_cast<cudaStream_t>(stream));
 }
 

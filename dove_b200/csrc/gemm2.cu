@@ -5,6 +5,8 @@
 // Same roles as gemm.cu: warp 0 TMA producer (both CTAs), warp 1 TMEM owner (both) + MMA issuer (leader),
 // warps 2..9 epilogue (both CTAs).  "full" barriers live in the leader; "empty" barriers are released in both CTAs by
 // multicast tcgen05.commit; accumulators are double-buffered in TMEM (2 x 256 columns).
+#include <mutex>
+
 #include "gemm_common.cuh"
 
 namespace dove {
@@ -146,13 +148,11 @@ int gemm2cta_launch(const void* A, long long lda, const void* W, long long ldw, 
   p.num_m_tiles = (M + 255) / 256;
   p.num_n_tiles = N / 256;
   p.num_kb = K / 64;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(Gemm2Cfg::SMEM));
-    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gemm2cta_kernel)");
-    attr_set = true;
-  }
+  static std::once_flag attr_once;   // thread-safe one-time opt-in to > 48 KB dynamic shared memory
+  cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [&] { attr_err = cudaFuncSetAttribute(gemm2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(Gemm2Cfg::SMEM)); });
+  if (attr_err != cudaSuccess) return check_cuda(attr_err, "cudaFuncSetAttribute(gemm2cta_kernel)");
   const int total = p.num_m_tiles * p.num_n_tiles;
   const int max_pairs = num_sms() / 2;
   const int pairs = total < max_pairs ? total : max_pairs;

@@ -28,7 +28,7 @@ struct GemmParams {
   const bf16* gate1;
   int split_row;
   int n_valid;    // columns stored
-  int out_mode;   // 0 row-major [rows, ldc], 1 planar [n][rows_total]
+  int out_mode;   // 0 row-major [rows, ldc]; planar [n][rows_total]: 1 bf16, 2 bf16 post-scaled to [0,1], 3 uint8
   long long rows_total;
   // fused GroupNorm statistics of the OUTPUT (consumed by the next GroupNorm): per-CTA partial sums
   float* gn_partial;   // [GN_PARTIAL_ROWS][32 groups][2] (sum, sum of squares) or nullptr
@@ -149,8 +149,18 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
     for (int i = 0; i < CH; ++i) {
       const int n = n0 + i;
       if (n < p.n_valid) {
-        if (p.out_mode == 0) p.C[row * p.ldc + n] = __float2bfloat16_rn(r[i]);
-        else p.C[static_cast<long long>(n) * p.rows_total + row] = __float2bfloat16_rn(r[i]);
+        if (p.out_mode == 0) {
+          p.C[row * p.ldc + n] = __float2bfloat16_rn(r[i]);
+        } else {
+          const long long o = static_cast<long long>(n) * p.rows_total + row;
+          if (p.out_mode == 1) {
+            p.C[o] = __float2bfloat16_rn(r[i]);
+          } else {   // fused post-processing of the last decoder conv: (x*0.5+0.5).clamp(0,1) with bf16 rounding points
+            const float v = fminf(fmaxf(bf16_round(bf16_round(bf16_round(r[i]) * 0.5f) + 0.5f), 0.0f), 1.0f);
+            if (p.out_mode == 2) p.C[o] = __float2bfloat16_rn(v);
+            else reinterpret_cast<uint8_t*>(p.C)[o] = static_cast<uint8_t>(v * 255.0f);   // trunc, as .to(uint8)
+          }
+        }
       }
     }
   }

@@ -11,7 +11,8 @@
 `process_video` is this package's implementation of ref :394-503 (same signature and semantics); it runs the
 fused device path (`one_step_sr`): pixels -> encoder -> sample*0.7 -> first-frame copy -> DiT -> x0 ->
 decoder -> *0.5+0.5 clamp, entirely through libdove_b200 kernels.  The reference's own `process_video` source
-also runs unmodified against this object (tests/test_reference_source.py).
+is run unmodified against this object on the GPU by tests/test_pipeline_gpu.py (fixture tests/golden/reference_process_video.py.txt,
+extracted by tests/golden/make_reference_source_fixture.py) and against the CPU oracle pipe by tests/test_reference_source.py.
 """
 from __future__ import annotations
 
@@ -101,19 +102,37 @@ class CogVideoXPipeline:
         z = latents.permute(0, 2, 1, 3, 4).contiguous()
         return self.vae.decode_scaled(z, 1.0 / self.vae_scaling_factor_image)
 
+    def _prompt_on_device(self, emb):
+        """[n_text, 4096] bf16 on the GPU.  The embedding is the same constant tensor for every unit of every clip
+        (ref :580-590), so its device copy is kept — which also lets the transformer keep `text_proj(emb)` cached."""
+        key = (emb.data_ptr(), emb._version, tuple(emb.shape), emb.dtype, str(emb.device))
+        hit = getattr(self, "_prompt_cache", None)
+        if hit is None or hit[0] != key:
+            d = emb.to(self.device, dtype=BF)
+            d = d.reshape(-1, d.shape[-1]).contiguous()
+            self._prompt_cache = hit = (key, emb, d)       # holding `emb` keeps the pointer key valid
+        return hit[2]
+
     # ---- fused one-step path ------------------------------------------------------------------------------
     @torch.no_grad()
     def one_step_sr(self, video, empty_prompt_embedding, sr_noise_step=399, noise=None, noise_step=0,
-                    return_intermediates=False):
-        """video [1,3,F,H,W] in [-1,1] (host or device, fp32/bf16) -> [1,3,F,H,W] bf16 in [0,1] on the GPU."""
+                    return_intermediates=False, output="unit", generator=None):
+        """video [1,3,F,H,W] in [-1,1] (host or device, fp32/bf16) -> [1,3,F,H,W] on the GPU: bf16 in [0,1]
+        (output="unit", what ref process_video returns) or uint8 = trunc(that*255) (output="uint8", what the
+        reference's savers make of it, ref :124/:143/:168 — the runner gathers / copies 1 byte per element).
+        `generator`: CUDA generator for every random draw of this unit (latent noise when `noise` is None, and the
+        add_noise draw when noise_step != 0); None = the global generator (reference semantics, ref :409, :449-457)."""
+        assert output in ("unit", "uint8")
         dev = self.device
         inter = {}
         video = video.to(dev, non_blocking=True)                                        # ref :407 (H2D)
         mom, (Tl, h, w) = self.vae.encode_cl(video if video.dtype in (torch.float32, BF) else video.to(BF))
         if noise is None:                                                               # ref :409 (global RNG)
-            noise = torch.randn((1, 16, Tl, h, w), device=dev, dtype=BF)
+            noise = torch.randn((1, 16, Tl, h, w), device=dev, dtype=BF, generator=generator)
         pt = self.transformer.config.patch_size_t
         ncopy = Tl % pt if pt is not None else 0                                        # ref :411-418
+        if pt is not None:
+            assert (Tl + ncopy) % pt == 0, "latent frames must be divisible by patch_size_t (ref :418)"
         z = torch.empty(16, Tl, h, w, dtype=BF, device=dev)
         L.gaussian_sample(mom, noise.contiguous(), z, Tl * h * w, self.vae_scaling_factor_image)
         latent = torch.empty(ncopy + Tl, 16, h, w, dtype=BF, device=dev)                # [F,16,h,w]  (ref :446)
@@ -122,10 +141,9 @@ class CogVideoXPipeline:
             latent[:ncopy] = z[:, :1].permute(1, 0, 2, 3)
         Fl = latent.shape[0]
         if noise_step != 0:                                                             # ref :449-457
-            n = torch.randn_like(latent)
+            n = torch.randn(latent.shape, device=dev, dtype=latent.dtype, generator=generator)
             latent = self.scheduler.add_noise(latent, n, torch.tensor([noise_step]))
-        emb = empty_prompt_embedding.to(dev, dtype=BF)                                  # ref :423-428
-        emb = emb.reshape(-1, emb.shape[-1])
+        emb = self._prompt_on_device(empty_prompt_embedding)                            # ref :423-428
         tc = self.transformer.config
         rope = None
         if tc.use_rotary_positional_embeddings:                                         # ref :467-480
@@ -139,14 +157,18 @@ class CogVideoXPipeline:
         L.unpatchify_velocity(tok, latent, x0, pred, Fl, 16, h, w, a, b)                 # ref :491-493
         x0 = x0[ncopy:]                                                                 # ref :496-497
         zdec = x0.permute(1, 0, 2, 3).contiguous()[None]                                # [1,16,Tl,h,w]
-        dec = self.vae.decode_scaled(zdec, 1.0 / self.vae_scaling_factor_image)         # ref :500
-        out = torch.empty_like(dec)
-        L.post_scale(dec, out)                                                          # ref :501
-        if return_intermediates:
+        inv = 1.0 / self.vae_scaling_factor_image
+        if return_intermediates:                                                        # raw decode kept for the tests
+            dec = self.vae.decode_scaled(zdec, inv)                                     # ref :500
+            out = torch.empty_like(dec)
+            L.post_scale(dec, out)                                                      # ref :501
+            if output == "uint8":
+                out = (out.float() * 255.0).to(torch.uint8)
             inter.update(moments=LazyMoments(mom, (Tl, h, w)), latent=latent[None], pred=pred[None], x0=x0[None],
                          decoded=dec)
             return out, inter
-        return out
+        # ref :500-501 in one pass: `*0.5+0.5, clamp` (and the savers' uint8 quantisation) run in the last conv's epilogue
+        return self.vae.decode_scaled(zdec, inv, post=output)
 
 
 class LazyMoments:

@@ -37,11 +37,34 @@ def _region_numel(r, C):
             (r["out_w_end"] - r["out_w_start"]))
 
 
+_DTYPE_NAMES = {"bfloat16": torch.bfloat16, "float32": torch.float32, "float16": torch.float16, "uint8": torch.uint8}
+_staging = {}
+
+
+def _unit_to_device(unit, dev):
+    """A unit is a strided view of the clip.  When the clip lives in (pinned) host memory only THIS unit crosses
+    PCIe: it is packed into a reusable pinned staging buffer and copied asynchronously (ref :407 copies per unit too)."""
+    dev = torch.device(dev)
+    if unit.device.type != "cpu" or dev.type != "cuda":
+        return unit.to(dev)
+    key = (tuple(unit.shape), unit.dtype)
+    buf = _staging.get(key)
+    if buf is None:
+        _staging.clear()                                   # one live staging shape at a time
+        buf = _staging[key] = torch.empty(unit.shape, dtype=unit.dtype).pin_memory()
+    torch.cuda.current_stream(dev).synchronize()           # the previous unit's async H2D has left the buffer
+    buf.copy_(unit)
+    return buf.to(dev, non_blocking=True)
+
+
 def super_resolve(video, process_fn, *, chunk_len=0, overlap_t=8, tile_size_hw=(0, 0), overlap_hw=(32, 32),
-                  out_device=None, out_dtype=None, group=None, noise_mode=None, seed=42):
-    """video: [1,3,F,H,W] float in [-1,1] (already x4-upscaled and padded, ref :670-679).
-    process_fn(unit_video, unit_index, generator_seed_or_None) -> [1,3,t,h,w] tensor in [0,1].
-    Returns the stitched [1,3,F,H,W] clip (on every rank when sharded)."""
+                  out_device=None, out_dtype=None, group=None, noise_mode=None, seed=42, timings=None):
+    """video: [1,3,F,H,W] float in [-1,1] (already x4-upscaled and padded, ref :670-679), on the host or the GPU.
+    process_fn(unit_video, unit_index, generator_seed_or_None) -> [1,3,t,h,w] tensor in [0,1] (or uint8 0..255);
+    it may declare `.out_dtype` / `.device` attributes (make_process_fn does) so that ranks WITHOUT units agree with
+    the working ranks on the gather buffer's dtype and device.
+    Returns the stitched [1,3,F,H,W] clip (on every rank when sharded).  `timings` (dict, optional) receives
+    compute_ms / collective_ms / units measured with CUDA events on this rank."""
     import torch.distributed as dist
     sharded = group is not None or (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
     rank = dist.get_rank(group) if sharded else 0
@@ -53,7 +76,17 @@ def super_resolve(video, process_fn, *, chunk_len=0, overlap_t=8, tile_size_hw=(
     B, C, F, H, W = video.shape
     units = enumerate_units(video.shape, chunk_len, overlap_t, tile_size_hw, overlap_hw)
     regions = _unit_regions(units, video.shape, overlap_t, overlap_hw)
-    mine = partition_units(units, world)[rank]
+    parts = partition_units(units, world)
+    mine = parts[rank]
+
+    # Output device / dtype must be the same on EVERY rank, including ranks that own no unit (fewer units than
+    # ranks): they are taken from the arguments or from what process_fn declares — never from a local result.
+    dev = torch.device(out_device or getattr(process_fn, "device", None) or video.device)
+    dt = out_dtype or getattr(process_fn, "out_dtype", None)
+    use_cuda_events = timings is not None and dev.type == "cuda"
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if use_cuda_events else None
+    if ev:
+        ev[0].record()
 
     results = {}
     for k in mine:
@@ -63,11 +96,19 @@ def super_resolve(video, process_fn, *, chunk_len=0, overlap_t=8, tile_size_hw=(
         r = regions[k]
         results[k] = res[:, :, r["valid_t_start"]:r["valid_t_end"], r["valid_h_start"]:r["valid_h_end"],
                          r["valid_w_start"]:r["valid_w_end"]]
-    any_res = next(iter(results.values())) if results else None
-    dev = out_device or (any_res.device if any_res is not None else video.device)
-    dt = out_dtype or (any_res.dtype if any_res is not None else video.dtype)
-    if world > 1:   # every rank must agree on dtype/device kind; they do by construction (same process_fn)
-        dev = out_device or (any_res.device if any_res is not None else torch.device("cpu"))
+    if ev:
+        ev[1].record()
+    if dt is None:
+        local = next(iter(results.values())).dtype if results else None
+        if world > 1:      # undeclared output dtype: agree on it explicitly (tiny host-side exchange)
+            names = [None] * world
+            dist.all_gather_object(names, str(local).replace("torch.", "") if local is not None else None, group=group)
+            seen = sorted({n for n in names if n is not None})
+            if len(seen) > 1:
+                raise StitchError(f"ranks disagree on the output dtype: {seen}")
+            dt = _DTYPE_NAMES[seen[0]] if seen else video.dtype
+        else:
+            dt = local if local is not None else video.dtype
 
     out = torch.zeros((B, C, F, H, W), dtype=dt, device=dev)
     count = torch.zeros((F, H, W), dtype=torch.int32, device=dev)
@@ -83,7 +124,6 @@ def super_resolve(video, process_fn, *, chunk_len=0, overlap_t=8, tile_size_hw=(
         for k, block in results.items():
             write(k, block)
     else:
-        parts = partition_units(units, world)
         lens = [sum(_region_numel(regions[k], B * C) for k in p) for p in parts]
         maxlen = max(max(lens), 1)
         send = torch.zeros(maxlen, dtype=dt, device=dev)
@@ -103,23 +143,31 @@ def super_resolve(video, process_fn, *, chunk_len=0, overlap_t=8, tile_size_hw=(
                 n = _region_numel(rg, B * C)
                 write(k, recv[off:off + n].view(shp))
                 off += n
+    if ev:
+        ev[2].record()
     if not bool((count == 1).all()):
         bad = int((count != 1).sum())
         raise StitchError(f"write count != 1 at {bad} positions (overlaps must be even and tiles must cover the clip)")
+    if timings is not None:
+        timings["units"] = len(mine)
+        if ev:
+            torch.cuda.synchronize(dev)
+            timings["compute_ms"] = ev[0].elapsed_time(ev[1])
+            timings["collective_ms"] = ev[1].elapsed_time(ev[2])     # pack + all-gather + unpack/stitch
     return out
 
 
-def make_process_fn(pipe, empty_prompt_embedding, sr_noise_step=399, noise_step=0):
-    """process_fn for `super_resolve` backed by the fused device path of `pipe`."""
+def make_process_fn(pipe, empty_prompt_embedding, sr_noise_step=399, noise_step=0, output="unit"):
+    """process_fn for `super_resolve` backed by the fused device path of `pipe`.  output="uint8": units come back
+    quantised as the reference's savers would (trunc(x*255)), so the gather and the D2H move 1 byte per element."""
     def fn(unit, k, unit_seed):
-        noise = None
-        if unit_seed is not None:
-            _, _, F, H, W = unit.shape
+        g = None
+        if unit_seed is not None:      # every random draw of this unit (latent noise, add_noise) is seeded per unit
             g = torch.Generator(device=pipe.device).manual_seed(int(unit_seed))
-            tl = pipe.vae.latent_frames(F)
-            noise = torch.randn((1, 16, tl, H // 8, W // 8), generator=g, device=pipe.device, dtype=torch.bfloat16)
-        return pipe.one_step_sr(unit, empty_prompt_embedding, sr_noise_step=sr_noise_step, noise=noise,
-                                noise_step=noise_step)
+        return pipe.one_step_sr(_unit_to_device(unit, pipe.device), empty_prompt_embedding,
+                                sr_noise_step=sr_noise_step, noise_step=noise_step, output=output, generator=g)
+    fn.out_dtype = torch.uint8 if output == "uint8" else torch.bfloat16
+    fn.device = pipe.device
     return fn
 
 

@@ -33,6 +33,28 @@ def _pad_to(n, m):
     return (n + m - 1) // m * m
 
 
+class _TrackedStateDict:
+    """Strict checkpoint access: a missing key raises with the component name, and any tensor the build did not
+    consume is an error (a silently dropped parameter would make every output wrong with released weights)."""
+
+    def __init__(self, sd, what):
+        self._sd, self._what, self._used = sd, what, set()
+
+    def __getitem__(self, k):
+        if k not in self._sd:
+            raise KeyError(f"{self._what} checkpoint is missing '{k}' (strict loading: no silent defaults)")
+        self._used.add(k)
+        return self._sd[k]
+
+    def __contains__(self, k):
+        return k in self._sd
+
+    def check_all_consumed(self):
+        extra = sorted(set(self._sd) - self._used)
+        if extra:
+            raise KeyError(f"{self._what} checkpoint has {len(extra)} unconsumed tensors, e.g. {extra[:4]}")
+
+
 class _Conv:
     """Weights of one conv in implicit-GEMM layout [Cout_pad, kt*kh*kw*Cin_pad], K index = tap*Cin_pad + c."""
 
@@ -138,6 +160,11 @@ class AutoencoderKLCogVideoX:
 
     # ---- weights ----------------------------------------------------------------------------------
     def _build(self, sd):
+        sd = _TrackedStateDict(sd, "vae")
+        self._build_from(sd)
+        sd.check_all_consumed()
+
+    def _build_from(self, sd):
         dev = self._device
         c = self.config
         boc = list(c.block_out_channels)
@@ -351,8 +378,10 @@ class AutoencoderKLCogVideoX:
         return SimpleNamespace(latent_dist=LatentDistribution(mom, shape))
 
     # ---- decoder ----------------------------------------------------------------------------------
-    def _decoder_batch(self, z, t0, t1, h, w, scale, cache, out, f_off, F_out):
-        """z: [16, Tz_total, h, w] bf16; latent frames t0..t1 -> pixels written into out[3, F_out, 8h, 8w]."""
+    def _decoder_batch(self, z, t0, t1, h, w, scale, cache, out, f_off, F_out, out_mode=L.OUT_PLANAR):
+        """z: [16, Tz_total, h, w] bf16; latent frames t0..t1 -> pixels written into out[3, F_out, 8h, 8w].
+        out_mode: L.OUT_PLANAR (raw decoder output), L.OUT_PLANAR_POST (`*0.5+0.5` clamp of ref :501 fused into the
+        last conv's epilogue) or L.OUT_PLANAR_U8 (that, quantised like the reference's savers; `out` is uint8)."""
         T = t1 - t0
         zsrc = z[:, t0:t1].contiguous()
         xin = self._empty(T, h, w, 64)
@@ -382,11 +411,11 @@ class AutoencoderKLCogVideoX:
         del x
         # conv_out writes planar NCDHW straight into the output clip at frame offset f_off
         self._causal_conv(self.dec_conv_out, xin2, T, H, W, cache, "conv_out",
-                          out=out.view(3, -1)[:, f_off * H * W:], out_mode=1, plane_stride=F_out * H * W)
+                          out=out.view(3, -1)[:, f_off * H * W:], out_mode=out_mode, plane_stride=F_out * H * W)
         return T
 
-    def _decode_untiled(self, zc, scale):
-        """zc [16,Tz,h,w] bf16 contiguous -> [1,3,F,8h,8w] bf16 (frame-batched, fresh conv cache)."""
+    def _decode_untiled(self, zc, scale, out_mode=L.OUT_PLANAR):
+        """zc [16,Tz,h,w] bf16 contiguous -> [1,3,F,8h,8w] bf16 / uint8 (frame-batched, fresh conv cache)."""
         _, Tz, h, w = zc.shape
         sf = 2 ** (len(self.config.block_out_channels) - 1)
         batches = self.frame_batches(Tz, self.num_latent_frames_batch_size)
@@ -396,11 +425,12 @@ class AutoencoderKLCogVideoX:
             for _ in range(2):
                 T = (1 + 2 * (T - 1) if T % 2 else 2 * T) if T > 1 else T
             F_out += T
-        out = self._empty(1, 3, F_out, h * sf, w * sf)
+        out = torch.empty(1, 3, F_out, h * sf, w * sf, device=self._device,
+                          dtype=torch.uint8 if out_mode == L.OUT_PLANAR_U8 else BF)
         cache = {}
         f_off = 0
         for (s, e) in batches:
-            f_off += self._decoder_batch(zc, s, e, h, w, scale, cache, out[0], f_off, F_out)
+            f_off += self._decoder_batch(zc, s, e, h, w, scale, cache, out[0], f_off, F_out, out_mode)
         return out
 
     def _decode_tiled(self, zc, scale):
@@ -419,15 +449,26 @@ class AutoencoderKLCogVideoX:
         out = self._empty(3, F_out, h * sf, w * sf)
         return self._blend_and_stitch(rows, dec, "planar", out)[None]
 
-    def decode_scaled(self, z, scale=1.0):
-        """z: [1,16,Tz,h,w] bf16 -> [1,3,F,8h,8w] bf16; `scale` is applied to z first (decode_latents' 1/0.7)."""
+    def decode_scaled(self, z, scale=1.0, post=None):
+        """z: [1,16,Tz,h,w] bf16 -> [1,3,F,8h,8w]; `scale` is applied to z first (decode_latents' 1/0.7).
+        post=None: raw decoder output (bf16, about [-1,1]); "unit": `(x*0.5+0.5).clamp(0,1)` (ref :501) bf16;
+        "uint8": that value quantised as the reference's savers do, trunc(x*255) (ref :124, :143, :168).
+        Untiled decodes fuse the post-processing into the last conv's epilogue; VAE-tiled decodes blend the raw
+        tiles first (diffusers order) and post-process afterwards."""
         assert z.dim() == 5 and z.shape[0] == 1 and z.shape[1] == 16
+        assert post in (None, "unit", "uint8")
         _, _, Tz, h, w = z.shape
         zc = z[0].to(BF).contiguous()
         _, dec = self.tile_ints()
         if self.use_tiling and (w > dec["tile_w"] or h > dec["tile_h"]):
-            return self._decode_tiled(zc, scale)
-        return self._decode_untiled(zc, scale)
+            raw = self._decode_tiled(zc, scale)
+            if post is None:
+                return raw
+            unit = torch.empty_like(raw)
+            L.post_scale(raw, unit)
+            return unit if post == "unit" else (unit.float() * 255.0).to(torch.uint8)
+        mode = {None: L.OUT_PLANAR, "unit": L.OUT_PLANAR_POST, "uint8": L.OUT_PLANAR_U8}[post]
+        return self._decode_untiled(zc, scale, mode)
 
     def decode(self, z):
         return SimpleNamespace(sample=self.decode_scaled(z.to(self._device), 1.0))

@@ -101,7 +101,10 @@ def dit_param_spec(cfg=None):
     dim = c["num_attention_heads"] * hd
     te = c["time_embed_dim"]
     pfeat = c["in_channels"] * c["patch_size"] ** 2 * c["patch_size_t"]
-    s = _linear("patch_embed.proj", pfeat, dim, c["patch_bias"]) + _linear("patch_embed.text_proj", c["text_embed_dim"], dim)
+    # CogVideoX-1.5 (patch_size_t set): diffusers builds the patch projection as nn.Linear with its default bias,
+    # whatever config.patch_bias says (it only applies to the 1.0 Conv2d branch) — the checkpoint has the tensor.
+    has_pbias = c["patch_size_t"] is not None or c["patch_bias"]
+    s = _linear("patch_embed.proj", pfeat, dim, has_pbias) + _linear("patch_embed.text_proj", c["text_embed_dim"], dim)
     s += _linear("time_embedding.linear_1", dim, te) + _linear("time_embedding.linear_2", te, te)
     for i in range(c["num_layers"]):
         b = f"transformer_blocks.{i}"

@@ -47,7 +47,9 @@ int dove_init(int device);
 const char* dove_last_error(void);
 int dove_num_sms(void);
 /* Tuning / test switches.  "conv2cta": 1 (default) = big stride-1 3x3(x3) convs on images >= 256 wide run on the
- * CTA-pair kernel (cta_group::2 MMA + in-smem reuse of the W taps), 0 = always the 1-CTA kernel (tests). */
+ * CTA-pair kernel (cta_group::2 MMA + in-smem reuse of the W taps), 0 = always the 1-CTA kernel (tests).
+ * "attn_variant": 0 = one query tile per CTA, two CTAs per SM (round-1 kernel); 1 + e (e = 0..5) = two query tiles
+ * per CTA sharing the K/V stages, with e/8 of the softmax exponentials evaluated on the FMA pipe (see attn.cu). */
 int dove_set_option(const char* name, int value);
 
 /* ---- DiT -------------------------------------------------------------------------------------------------- */
@@ -82,7 +84,7 @@ int dove_qk_norm_rope_bf16(void* qkv, int rows, int heads, const void* q_w, cons
                            const void* k_b, float eps, const float* cos, const float* sin, int text_len,
                            void* stream);
 
-/* out[rows, heads*64] = softmax(q k^T / 8) v per head, non-causal, no mask.  q,k,v read from the fused
+/* out[rows, heads*64] = softmax(q k^T * scale) v per head, non-causal, no mask.  q,k,v read from the fused
  * qkv [rows, 3*heads*64] buffer.  tcgen05 flash-attention kernel (S, P and O in TMEM, lazy rescaling).
  * F.scaled_dot_product_attention in CogVideoXAttnProcessor2_0. */
 int dove_attention_bf16(const void* qkv, void* out, int rows, int heads, float scale, void* stream);
@@ -105,10 +107,14 @@ int dove_velocity_bf16(const void* sample, const void* noise, void* out, int64_t
 
 /* Implicit-GEMM convolution on channels-last bf16, tcgen05 + TMA (no im2col buffer).
  *   x: [Tin, Hin, Win, Cin], Cin % 64 == 0.  For causal 3x3x3 convs the caller provides the temporally padded
- *      input (Tin = Tout + 2: two cached / replicated frames first), see dove_causal_pad_frames.
+ *      input (Tin = Tout + 2: two cached / replicated frames first); dove_conv3d_causal_bf16 below avoids that copy.
  *   w: [Cout_pad, kt*kh*kw*Cin] bf16, K index = ((dt*kh + dh)*kw + dw)*Cin + c; Cout_pad % 16 == 0.
  *   y: out_mode 0: [Tout, Ho, Wo, ldy] channels-last (ldy >= cout_valid); out_mode 1: planar, element (n, voxel) at y[n*ldy + voxel]
  *      (ldy = plane stride >= Tout*Ho*Wo: lets a frame batch land inside a longer NCDHW clip).
+ *      out_mode 2: planar like 1 with the reference's post-processing fused (ref: inference_script.py:501):
+ *      bf16 clamp(bf16(bf16(r*0.5)+0.5), 0, 1).  out_mode 3: the same value quantised as the reference's savers do
+ *      (ref: inference_script.py:124, 143, 168: `(video*255).clamp(0,255).to(uint8)` on the fp32 copy): y is uint8,
+ *      y[n*ldy + voxel] = trunc(fp32(v) * 255) — the multi-GPU gather and the D2H then move 1 byte per element.
  *   stride: spatial stride (1 or 2); pad: low-side spatial zero pad (1 for "same" 3x3, 0 for the
  *   CogVideoXDownsample3D conv whose (0,1,0,1) pad is right/bottom only — high-side pad comes from TMA OOB fill).
  *   epilogue: DOVE_EPI_BIAS or DOVE_EPI_ADD (aux: [Tout,Ho,Wo,ld_aux]).
@@ -150,12 +156,6 @@ int dove_gn_finalize(const float* partial, int64_t nvox, int C, int groups, floa
 int dove_gn_apply_bf16(const void* x, void* out, int T, int H, int W, int C, int groups, const float* stats,
                        const void* gamma, const void* beta, int apply_silu, const void* zq_y, const void* zq_b,
                        int Tz, int hz, int wz, void* stream);
-
-/* Fill the 2 leading frames of a temporally padded conv input xin [T+2, H, W, C]: from `cache` ([2,H,W,C]) when
- * non-NULL, else by replicating frame xin[2]; then save xin[T:T+2] into new_cache (may equal cache).
- * CogVideoXCausalConv3d.fake_context_parallel_forward + conv_cache. */
-int dove_causal_pad_frames(void* xin, int T, int64_t frame_elems, const void* cache, void* new_cache,
-                           void* stream);
 
 /* Temporal average pooling of CogVideoXDownsample3D(compress_time): T odd -> keep frame 0, avg pairs of the
  * rest; T even -> avg pairs.  x [T, HWC] -> y [Tout, HWC]. */

@@ -96,7 +96,10 @@ class PatchEmbed(nn.Module):
     def __init__(self, p, p_t, cin, dim, text_dim, bias):
         super().__init__()
         self.p, self.p_t = p, p_t
-        self.proj = nn.Linear(cin * p * p * p_t, dim, bias=bias)
+        # diffusers CogVideoXPatchEmbed: the CogVideoX-1.5 branch (patch_size_t is not None) builds
+        # nn.Linear(in*p*p*p_t, dim) with the DEFAULT bias (the `bias` / config.patch_bias argument only reaches the
+        # 1.0 Conv2d branch), and the released 1.5 checkpoints ship a trained patch_embed.proj.bias.
+        self.proj = nn.Linear(cin * p * p * p_t, dim, bias=True if p_t is not None else bias)
         self.text_proj = nn.Linear(text_dim, dim)
 
     def forward(self, text, image):

@@ -40,3 +40,10 @@ def b200_pipe(vsd, dsd, dit_cfg, device="cuda"):
     from dove_b200.vae import AutoencoderKLCogVideoX
     return CogVideoXPipeline(AutoencoderKLCogVideoX(vsd, None, device),
                              CogVideoXTransformer3DModel(dsd, dit_cfg, device))
+
+
+def prompt_embedding(device="cpu"):
+    """The reference's shipped empty-prompt T5 embedding [226, 4096] bf16 (tests/golden fixture, ref :580-590)."""
+    from pathlib import Path
+    from dove_b200.pipeline import load_prompt_embedding
+    return load_prompt_embedding(Path(__file__).resolve().parent / "golden" / "empty_prompt_embedding.safetensors").to(device)

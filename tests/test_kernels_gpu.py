@@ -125,6 +125,17 @@ def test_conv_planar_out(L):
     torch.cuda.synchronize()
     ref = conv_ref(x, w[:3], bias[:3], 3, 3, 3, 1, 1, cin, 3).permute(3, 0, 1, 2)
     assert rel_l2(y, rb(ref)) < TOL
+    # fused post-processing epilogues (ref inference_script.py:501 and the savers' uint8 quantisation :124/:143/:168):
+    # bit-exact functions of the raw bf16 output of the same kernel
+    y2 = torch.empty_like(y)
+    L.conv_cl(x, w, bias, y2, T, 3, 3, 3, 1, 1, H, W, 3, out_mode=L.OUT_PLANAR_POST)
+    y3 = torch.empty((3, T, H, W), device="cuda", dtype=torch.uint8)
+    L.conv_cl(x, w, bias, y3, T, 3, 3, 3, 1, 1, H, W, 3, out_mode=L.OUT_PLANAR_U8)
+    torch.cuda.synchronize()
+    unit = (y * 0.5 + 0.5).clamp(0.0, 1.0)                   # torch bf16 ops, as the reference applies them
+    assert torch.equal(y2, unit)
+    assert torch.equal(y3, (unit.float() * 255).clamp(0, 255).to(torch.uint8))
+    assert 0 < y3.float().mean().item() < 255
 
 
 @pytest.mark.parametrize("rows,heads", [(128, 1), (200, 2), (482, 3), (1000, 2), (2304, 4), (19426, 2)])
@@ -140,6 +151,59 @@ def test_attention(L, rows, heads):
     e = rel_l2(out, ref)
     print(f"attention rows{rows} heads{heads}: rel_l2={e:.3e}")
     assert e < 5e-3    # P is rounded to bf16 before the PV matmul (as flash SDPA does)
+
+
+def _attn_ref(qkv, rows, heads, scale):
+    q, k, v = [t.float().reshape(rows, heads, 64).transpose(0, 1) for t in qkv.chunk(3, dim=1)]
+    p = torch.softmax(q @ k.transpose(1, 2) * scale, dim=-1)
+    return (p @ v).transpose(0, 1).reshape(rows, heads * 64)
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("rows,heads", [(128, 1), (300, 2), (482, 3), (1000, 2), (4000, 2)])
+def test_attention_variants(L, variant, rows, heads):
+    """Every attention kernel variant (v2: one query tile per CTA; v3: two query tiles per CTA sharing K/V, with 0..5/8
+    of the exponentials on the FMA-pipe polynomial) against fp32 softmax attention, ragged sizes included."""
+    L.set_option("attn_variant", variant)
+    try:
+        qkv = randn(rows, 3 * heads * 64, seed=rows + 1)
+        out = torch.full((rows, heads * 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+        L.attention(qkv, out, heads, 0.125)
+        torch.cuda.synchronize()
+        assert torch.isfinite(out.float()).all()
+        e = rel_l2(out, _attn_ref(qkv, rows, heads, 0.125))
+        print(f"attention variant{variant} rows{rows} heads{heads}: rel_l2={e:.3e}")
+        assert e < 5e-3
+    finally:
+        L.set_option("attn_variant", L.DEFAULT_ATTN_VARIANT)
+
+
+@pytest.mark.parametrize("variant", [0, 3, 5])
+def test_attention_wide_logit_range(L, variant):
+    """Scores spanning tens of nats, a dominant key that appears only in the LAST key tile and one far-below-everything
+    key: the steady-state softmax (no row-max pass, stale reference max) must detect the overflow through the row sum
+    and fall back to the exact rescaling path; far-negative scores must not break the FMA-pipe exponential."""
+    rows, heads = 1500, 2
+    L.set_option("attn_variant", variant)
+    try:
+        g = torch.Generator(device="cuda").manual_seed(5)
+        q = torch.randn(rows, heads * 64, generator=g, device="cuda") * 3
+        k = torch.randn(rows, heads * 64, generator=g, device="cuda") * 3
+        v = torch.randn(rows, heads * 64, generator=g, device="cuda")
+        k[-3] = q[7] * 4                      # a late key that dominates (at least) query 7
+        k[5] = -q[9] * 40                     # ~ -1e4 nats for query 9: far below the clamp of the polynomial path
+        qkv = bf(torch.cat([q, k, v], dim=1))
+        out = torch.full((rows, heads * 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+        L.attention(qkv, out, heads, 0.125)
+        torch.cuda.synchronize()
+        assert torch.isfinite(out.float()).all()
+        ref = _attn_ref(qkv, rows, heads, 0.125)
+        e = rel_l2(out, ref)
+        print(f"attention wide-range variant{variant}: rel_l2={e:.3e}")
+        assert e < 1e-2
+        assert rel_l2(out[7], ref[7]) < 1e-2
+    finally:
+        L.set_option("attn_variant", L.DEFAULT_ATTN_VARIANT)
 
 
 def test_layernorm_mod(L):

@@ -9,9 +9,57 @@ from oracle.vae import CausalConv3d, OracleAutoencoderKLCogVideoX
 
 def test_parameter_count_pin():
     v, d = param_count(vae_param_spec()), param_count(dit_param_spec())
-    assert v == 215_583_907 and d == 5_570_673_280
+    assert v == 215_583_907 and d == 5_570_676_352      # incl. patch_embed.proj.bias (3072)
     published = 5787.19e6            # assets/Quantitative-2.png
     assert abs((v + d) - published) / published < 5e-4
+
+
+def test_published_mac_count_pin():
+    """assets/Quantitative-2.png: 504.81 T MACs for DOVE at 33x720x1280 (module MACs: the SDPA core is not counted).
+    The analytic model of the restated architecture gives 504.60 T (0.04 %), SURVEY.md section 6 / 8c pin (2)."""
+    from dove_b200.workmodel import clip_macs
+    m = clip_macs(33, 720, 1280)
+    assert m["tokens"] == 18226
+    assert abs(m["module_macs"] / 1e12 - 504.81) / 504.81 < 1e-3
+    assert abs(m["module_macs"] / 1e12 - 504.60) < 0.01
+    # SURVEY 8d FLOP table (2 * MACs, SDPA core included): cfg-1, cfg-2, cfg-4 chunk
+    for shape, tflop in (((8, 256, 256), 19.0), ((33, 768, 1280), 1271.1), ((25, 1088, 1920), 2309.6)):
+        assert abs(2 * clip_macs(*shape)["total"] / 1e12 - tflop) < 0.06, shape
+
+
+def test_prompt_embedding_fixture():
+    """The shipped pre-computed T5 embedding of "" (ref :580-590): key, shape, dtype and statistics."""
+    import hashlib
+    from pathlib import Path
+    from safetensors.torch import load_file
+    f = Path(__file__).resolve().parent / "golden" / "empty_prompt_embedding.safetensors"
+    sd = load_file(str(f))
+    assert list(sd) == ["prompt_embedding"]
+    t = sd["prompt_embedding"]
+    assert t.shape == (226, 4096) and t.dtype == torch.bfloat16
+    assert abs(t.float().mean().item() - 0.00175) < 1e-4 and abs(t.float().std().item() - 0.1485) < 1e-3
+    assert abs(t.float().abs().max().item() - 6.47) < 0.01
+    assert hashlib.sha256(f.read_bytes()).hexdigest() == "49738b5f634bc7c7ebad8e0ba01bf8c4eb5930b84c38d00f78dc0d5bc0a417cc"
+
+
+def test_strict_checkpoint_keys():
+    """A checkpoint tensor the build does not consume (or a missing one) must raise, never be dropped silently
+    (the CogVideoX-1.5 patch_embed.proj.bias exists although config.patch_bias is false)."""
+    names = {n for n, _, _ in dit_param_spec()}
+    assert "patch_embed.proj.bias" in names and "patch_embed.proj.weight" in names
+    from dove_b200.vae import _TrackedStateDict
+    sd = _TrackedStateDict({"a": 1, "b": 2}, "vae")
+    assert sd["a"] == 1 and "b" in sd
+    try:
+        sd.check_all_consumed()
+        raise AssertionError("unconsumed key not reported")
+    except KeyError as e:
+        assert "unconsumed" in str(e)
+    try:
+        sd["c"]
+        raise AssertionError("missing key not reported")
+    except KeyError as e:
+        assert "missing" in str(e)
 
 
 def test_spec_matches_oracle_modules():
