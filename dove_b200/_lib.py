@@ -38,6 +38,9 @@ _SIGS = {
                                         c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "dove_qk_norm_rope_bf16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
                                        c_void_p, c_void_p, c_int, c_void_p]),
+    "dove_gemm_qkv_norm_rope_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int,
+                                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p,
+                                             c_void_p, c_int, c_void_p]),
     "dove_attention_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
     "dove_patchify_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "dove_unpatchify_velocity_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
@@ -172,6 +175,19 @@ def qk_norm_rope(qkv, heads, q_w, q_b, k_w, k_b, eps, cos, sin, text_len):
     _call("dove_qk_norm_rope_bf16", _p(_bf16c(qkv)), rows, heads, _p(q_w), _p(q_b), _p(k_w), _p(k_b), eps, _p(cos),
           _p(sin), text_len, _stream())
     return qkv
+
+
+def gemm_qkv_norm_rope(a, w, out, bias, heads, q_w, q_b, k_w, k_b, eps, cos, sin, text_len):
+    """out[M, 3*heads*64] = qkv projection with per-head q/k LayerNorm + RoPE fused in the GEMM epilogue."""
+    M, K = a.shape
+    assert a.dtype == w.dtype == out.dtype == torch.bfloat16 and a.stride(1) == 1 and out.stride(1) == 1
+    assert tuple(w.shape) == (3 * heads * 64, K) and tuple(out.shape) == (M, 3 * heads * 64)
+    if cos is not None:
+        assert cos.dtype == torch.float32 and cos.is_contiguous() and cos.shape == (M - text_len, 64)
+        assert sin.dtype == torch.float32 and sin.is_contiguous() and sin.shape == cos.shape
+    _call("dove_gemm_qkv_norm_rope_bf16", _p(a), a.stride(0), _p(w), w.stride(0), _p(out), out.stride(0), M, heads, K,
+          _p(_bf16c(bias)), _p(q_w), _p(q_b), _p(k_w), _p(k_b), eps, _p(cos), _p(sin), text_len, _stream())
+    return out
 
 
 def attention(qkv, out, heads, scale):

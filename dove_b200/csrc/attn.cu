@@ -267,8 +267,9 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
 // v3: ONE CTA PER SM, TWO 128-row query tiles per CTA (256 query rows) that share every staged K/V tile, so the
 // L2 -> SM traffic per query row is half of v2's, and a leaner softmax:
 //   * no row-max pass in the steady state: the exponent reference m_used is kept from earlier tiles and the
-//     probabilities are computed directly; the row sum of the tile detects the (rare) case where a score exceeded
-//     m_used by more than 8 log2 units (p > 2^8) and only then the exact path (max, rescale of O in TMEM) is run.
+//     probabilities are computed directly; the row sum of the tile (and the largest argument of the FMA-pipe
+//     exponential) detects the rare case where a score exceeded m_used by more than 64 log2 units, and only then the
+//     exact path (row max, rescale of O in TMEM) is run.
 //     The first KV tile and a ragged last tile always take the exact path.
 //   * the MUFU unit (16 ex2/clk/SM) bounds a head_dim-64 attention at 50 % tensor pipe, so EMU8/8 of the exponentials
 //     are evaluated on the FMA pipe instead (Cody-Waite split with the 1.5*2^23 magic add + a degree-3 minimax
@@ -279,7 +280,13 @@ attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
 // TMEM (512 columns): tile t at base + 256 t:  S = +0..127 (fp32), O = +128..191 (fp32), P = +192..255 (bf16 pairs).
 constexpr int A3_STAGES = 3;
 constexpr size_t A3_SMEM = 1024 + ATT_TILE_BYTES * (2 + 2 * A3_STAGES) + 256;
-constexpr float A3_OVERFLOW = 256.0f;   // 2^ATT_LAZY_THRESHOLD
+// Steady-state validity bound: the stale reference may lag the true row max by up to 2^6 = 64 log2 units before the tile is
+// redone exactly.  Nothing needs the probabilities to be <= 1: P is bf16 (fp32 exponent range), S/P/O/l are fp32, and
+// p <= 2^64 keeps every partial sum (128 keys x 152 tiles x |v|) far below fp32 overflow.  A TIGHT bound would be wrong
+// here: with a sum threshold of 2^8 a row whose first key tile (the 226 text tokens) scores a few units below the video
+// keys would take the exact path on every later tile (measured: 2x slower on the real DiT activations).
+constexpr float A3_SUM_LIMIT = 1.8446744e19f * 128.0f;   // 128 keys x 2^64
+constexpr float A3_ARG_LIMIT = 12582912.0f + 64.0f;      // magic-shifted exponent argument of the FMA-pipe path
 
 __host__ __device__ constexpr bool a3_emu_pair(int i, int emu8) { return ((i * emu8) % 8) < emu8 && emu8 > 0; }
 
@@ -475,7 +482,7 @@ attn_fwd_v3_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
         unpack_f32x2(lsB, b0, b1);
         lsum = (a0 + a1) + (b0 + b1);
         // a score more than 8 log2 units above m_used (or a NaN) shows up in the row sum: redo this tile exactly
-        exact = __any_sync(0xffffffffu, !(lsum <= A3_OVERFLOW) || tmax > 12582912.0f + 127.0f);
+        exact = __any_sync(0xffffffffu, !(lsum <= A3_SUM_LIMIT) || tmax > A3_ARG_LIMIT);
       }
       float alpha = 1.0f;
       if (exact) {

@@ -357,6 +357,77 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
   }
 }
 
+// SpatialNorm3D apply for the CogVideoX decoder, where the latent is upsampled by G = W / wz in x (G = 1, 2, 4, 8): a
+// thread owns ONE 8-channel column and G CONSECUTIVE voxels per step, which all share one conv_y / conv_b vector of the
+// latent row — those two vectors are loaded once per G voxels and stay PACKED: `bf16(bf16(n * y) + b)` is exactly what
+// HMUL2.BF16 / HADD2.BF16 compute (one rounding of the exact product / sum), so the per-element unpack + fp32 multiply +
+// re-round chain of the generic kernel (which made this variant issue-bound at 0.48 of HBM speed) disappears.
+template <int G>
+__global__ void __launch_bounds__(256) gn_apply_spatial_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int T,
+                                                               int H, int W, int C, int groups,
+                                                               const float* __restrict__ stats,
+                                                               const bf16* __restrict__ gamma,
+                                                               const bf16* __restrict__ beta, int apply_silu,
+                                                               const bf16* __restrict__ zy, const bf16* __restrict__ zb,
+                                                               int Tz, int hz, int wz) {
+  const int vcols = C >> 3;
+  const int cpg = C / groups;
+  const int vcol = threadIdx.x % vcols;
+  const int c0 = vcol * 8;
+  float a[8], b[8];
+  {
+    float g[8], bt[8];
+    unpack8(*reinterpret_cast<const uint4*>(gamma + c0), g);
+    unpack8(*reinterpret_cast<const uint4*>(beta + c0), bt);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int grp = (c0 + k) / cpg;
+      const float mean = stats[grp * 2], rstd = stats[grp * 2 + 1];
+      a[k] = rstd * g[k];
+      b[k] = bt[k] - mean * a[k];
+    }
+  }
+  const int gper = 256 / vcols;                 // voxel groups of a row covered per block pass
+  const int g0 = threadIdx.x / vcols;
+  const int rows = T * H;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int tf = row / H, yh = row - tf * H;
+    int tz;
+    if (T > 1 && (T & 1)) tz = (tf == 0) ? 0 : 1 + ((tf - 1) * (Tz - 1)) / (T - 1);
+    else tz = (tf * Tz) / T;
+    const int yz = (yh * hz) / H;
+    const long long zo = (static_cast<long long>(tz) * hz + yz) * wz * C + c0;
+    const bf16* xr = x + static_cast<long long>(row) * W * C + c0;
+    bf16* orow = out + static_cast<long long>(row) * W * C + c0;
+    for (int xz = g0; xz < wz; xz += gper) {
+      uint4 raw[G];
+#pragma unroll
+      for (int u = 0; u < G; ++u) raw[u] = *reinterpret_cast<const uint4*>(xr + static_cast<long long>(xz * G + u) * C);
+      const uint4 y4 = *reinterpret_cast<const uint4*>(zy + zo + static_cast<long long>(xz) * C);
+      const uint4 b4 = *reinterpret_cast<const uint4*>(zb + zo + static_cast<long long>(xz) * C);
+      const uint32_t yw[4] = {y4.x, y4.y, y4.z, y4.w}, bw[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int u = 0; u < G; ++u) {
+        float f[8];
+        unpack8(raw[u], f);
+        uint32_t w4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          __nv_bfloat162 n2 = __floats2bfloat162_rn(f[2 * k] * a[2 * k] + b[2 * k], f[2 * k + 1] * a[2 * k + 1] + b[2 * k + 1]);
+          n2 = __hadd2(__hmul2(n2, *reinterpret_cast<const __nv_bfloat162*>(&yw[k])),
+                       *reinterpret_cast<const __nv_bfloat162*>(&bw[k]));
+          if (apply_silu) {
+            const float2 v2 = __bfloat1622float2(n2);
+            n2 = __floats2bfloat162_rn(silu_fast(v2.x), silu_fast(v2.y));
+          }
+          w4[k] = *reinterpret_cast<uint32_t*>(&n2);
+        }
+        *reinterpret_cast<uint4*>(orow + static_cast<long long>(xz * G + u) * C) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ resampling
 __global__ void time_pool_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int T, long long fvec) {
   const int odd = T & 1;
@@ -655,6 +726,21 @@ extern "C" int dove_gn_apply_bf16(const void* x, void* out, int T, int H, int W,
   }
   const int rows = T * H;
   const int blocks = rows < num_sms() * 8 ? rows : num_sms() * 8;
+  if (zq_y && x_shift >= 0 && x_shift <= 3 && (wz << x_shift) == W) {     // CogVideoX decoder ratios 1, 2, 4, 8
+#define DOVE_GN_SPATIAL(G)                                                                                          \
+  gn_apply_spatial_kernel<G><<<blocks, 256, 0, ST(stream)>>>(                                                       \
+      static_cast<const bf16*>(x), static_cast<bf16*>(out), T, H, W, C, groups, stats, static_cast<const bf16*>(gamma), \
+      static_cast<const bf16*>(beta), apply_silu, static_cast<const bf16*>(zq_y), static_cast<const bf16*>(zq_b), Tz, hz, wz)
+    switch (x_shift) {
+      case 0: DOVE_GN_SPATIAL(1); break;
+      case 1: DOVE_GN_SPATIAL(2); break;
+      case 2: DOVE_GN_SPATIAL(4); break;
+      default: DOVE_GN_SPATIAL(8); break;
+    }
+#undef DOVE_GN_SPATIAL
+    DOVE_LAUNCH_CHECK("gn_apply_spatial_kernel");
+    return DOVE_OK;
+  }
   gn_apply_kernel<4><<<blocks, 256, 0, ST(stream)>>>(
       static_cast<const bf16*>(x), static_cast<bf16*>(out), T, H, W, C, groups, stats, static_cast<const bf16*>(gamma),
       static_cast<const bf16*>(beta), apply_silu, static_cast<const bf16*>(zq_y), static_cast<const bf16*>(zq_b), Tz, hz,

@@ -107,12 +107,25 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
       const bf16* gate = (p.epi == DOVE_EPI_GATED_RES) ? (row < p.split_row ? p.gate0 : p.gate1) : nullptr;
+      if (p.epi == DOVE_EPI_QKV_NORM_ROPE) {
+        // the 256-column tile holds 4 heads (64 columns each, all q, all k or all v since heads*64 % 256 == 0); the
+        // two epilogue warps of a lane quarter take heads {0, 2} and {1, 3}, so one thread owns whole heads of its row
 #pragma unroll 1
-      for (int c0 = half * CH; c0 < BN; c0 += 2 * CH) {
-        uint32_t v[CH];
-        tmem_ld32(t_row + c0, v);
-        tmem_ld_wait();
-        if (valid) epilogue_chunk<CH>(p, v, row, nt * BN + c0, gate);
+        for (int hh = half; hh < 4; hh += 2) {
+          uint32_t v[64];
+          tmem_ld32(t_row + hh * 64, v);
+          tmem_ld32(t_row + hh * 64 + 32, v + 32);
+          tmem_ld_wait();
+          if (valid) qkv_head_epilogue(p, v, row, nt * BN + hh * 64);
+        }
+      } else {
+#pragma unroll 1
+        for (int c0 = half * CH; c0 < BN; c0 += 2 * CH) {
+          uint32_t v[CH];
+          tmem_ld32(t_row + c0, v);
+          tmem_ld_wait();
+          if (valid) epilogue_chunk<CH>(p, v, row, nt * BN + c0, gate);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -162,3 +175,40 @@ int gemm2cta_launch(const void* A, long long lda, const void* W, long long ldw, 
 }
 
 }  // namespace dove
+
+// QKV projection with the per-head q/k LayerNorm and the 3-D RoPE applied in the GEMM epilogue (one head = 64
+// accumulator columns = one thread's registers), so the separate in-place pass over the [rows, 3*heads*64] buffer
+// (dove_qk_norm_rope_bf16) disappears from the DiT block.
+extern "C" int dove_gemm_qkv_norm_rope_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc,
+                                            int M, int heads, int K, const void* bias, const void* q_w, const void* q_b,
+                                            const void* k_w, const void* k_b, float eps, const float* cos,
+                                            const float* sin, int text_len, void* stream) {
+  using namespace dove;
+  if (int e = ensure_init()) return e;
+  const int N = 3 * heads * 64;
+  DOVE_CHECK_ARG(M > 0 && heads > 0 && K > 0 && K % 64 == 0, "gemm_qkv: bad shape M=%d heads=%d K=%d", M, heads, K);
+  DOVE_CHECK_ARG((heads * 64) % 256 == 0, "gemm_qkv: heads*64 = %d must be a multiple of 256", heads * 64);
+  DOVE_CHECK_ARG(lda % 8 == 0 && ldw % 8 == 0 && ldc % 8 == 0, "gemm_qkv: leading dims must be multiples of 8");
+  DOVE_CHECK_ARG((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(C)) % 16 == 0,
+                 "gemm_qkv: pointers must be 16-byte aligned");
+  DOVE_CHECK_ARG(bias && q_w && q_b && k_w && k_b, "gemm_qkv: bias and norm_q / norm_k parameters required");
+  DOVE_CHECK_ARG(text_len >= M || (cos && sin), "gemm_qkv: cos/sin tables required");
+  GemmParams p{};
+  p.M = M;
+  p.epi = DOVE_EPI_QKV_NORM_ROPE;
+  p.C = static_cast<bf16*>(C);
+  p.ldc = ldc;
+  p.bias = static_cast<const bf16*>(bias);
+  p.n_valid = N;
+  p.rows_total = M;
+  p.qk_w[0] = static_cast<const bf16*>(q_w);
+  p.qk_b[0] = static_cast<const bf16*>(q_b);
+  p.qk_w[1] = static_cast<const bf16*>(k_w);
+  p.qk_b[1] = static_cast<const bf16*>(k_b);
+  p.rope_cos = cos;
+  p.rope_sin = sin;
+  p.text_len = text_len;
+  p.heads = heads;
+  p.qk_eps = eps;
+  return gemm2cta_launch(A, lda, W, ldw, M, N, K, p, static_cast<cudaStream_t>(stream));
+}

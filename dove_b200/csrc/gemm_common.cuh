@@ -30,6 +30,13 @@ struct GemmParams {
   int n_valid;    // columns stored
   int out_mode;   // 0 row-major [rows, ldc]; planar [n][rows_total]: 1 bf16, 2 bf16 post-scaled to [0,1], 3 uint8
   long long rows_total;
+  // DOVE_EPI_QKV_NORM_ROPE (dense CTA-pair GEMM only): per-head LayerNorm(64) on the q / k column blocks + 3-D RoPE
+  const bf16* qk_w[2];   // norm_q.weight, norm_k.weight  [64]
+  const bf16* qk_b[2];   // norm_q.bias,   norm_k.bias    [64]
+  const float* rope_cos; // [rows - text_len, 64] fp32 (may be null when text_len >= rows)
+  const float* rope_sin;
+  int text_len, heads;
+  float qk_eps;
   // fused GroupNorm statistics of the OUTPUT (consumed by the next GroupNorm): per-CTA partial sums
   float* gn_partial;   // [GN_PARTIAL_ROWS][32 groups][2] (sum, sum of squares) or nullptr
   int gn_cpg;          // channels per group of the output tensor
@@ -163,6 +170,82 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
         }
       }
     }
+  }
+}
+
+// Epilogue of the fused QKV projection for ONE head (64 consecutive output columns col0.. of row `row`):
+//   r = bf16(acc + bias)                                           (nn.Linear to_q / to_k / to_v)
+//   q, k heads:  y = bf16(LayerNorm_64(r; w, b, eps))              (Attention.norm_q / norm_k, fp32 statistics)
+//                rows >= text_len:  y = bf16(y*cos + rot(y)*sin)   (apply_rotary_emb, fp32, interleaved pairs)
+//   v heads:     y = r
+// One thread owns the whole head of its row, so the statistics need no shuffles.
+__device__ __forceinline__ void qkv_head_epilogue(const GemmParams& p, const uint32_t* v, long long row, int col0) {
+  float r[64];
+  {
+    const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint4 b4 = bp[j];
+      const uint32_t bu[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 b2 = unpack_bf16x2(bu[k]);
+        r[j * 8 + 2 * k] = bf16_round(__uint_as_float(v[j * 8 + 2 * k]) + b2.x);
+        r[j * 8 + 2 * k + 1] = bf16_round(__uint_as_float(v[j * 8 + 2 * k + 1]) + b2.y);
+      }
+    }
+  }
+  const int which = col0 / (p.heads * 64);          // 0 = q, 1 = k, 2 = v
+  if (which < 2) {
+    float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 64; ++i) s4[i & 3] += r[i];
+    const float mean = ((s4[0] + s4[1]) + (s4[2] + s4[3])) * (1.0f / 64.0f);
+    float q4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+      r[i] -= mean;
+      q4[i & 3] += r[i] * r[i];
+    }
+    const float rstd = rsqrtf(((q4[0] + q4[1]) + (q4[2] + q4[3])) * (1.0f / 64.0f) + p.qk_eps);
+    const uint4* wp = reinterpret_cast<const uint4*>(p.qk_w[which]);
+    const uint4* bp = reinterpret_cast<const uint4*>(p.qk_b[which]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint4 w4 = wp[j], b4 = bp[j];
+      const uint32_t wu[4] = {w4.x, w4.y, w4.z, w4.w}, bu[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 w2 = unpack_bf16x2(wu[k]), b2 = unpack_bf16x2(bu[k]);
+        const int i = j * 8 + 2 * k;
+        r[i] = bf16_round(r[i] * rstd * w2.x + b2.x);
+        r[i + 1] = bf16_round(r[i + 1] * rstd * w2.y + b2.y);
+      }
+    }
+    if (row >= p.text_len) {      // out = x*cos + rot(x)*sin, rot(x)[2i] = -x[2i+1], rot(x)[2i+1] = x[2i]  (no fma)
+      const float4* cp = reinterpret_cast<const float4*>(p.rope_cos + (row - p.text_len) * 64);
+      const float4* sp = reinterpret_cast<const float4*>(p.rope_sin + (row - p.text_len) * 64);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float4 c4 = cp[j], s4v = sp[j];
+        const int i = j * 4;
+        const float a0 = r[i], a1 = r[i + 1], a2 = r[i + 2], a3 = r[i + 3];
+        r[i] = __fadd_rn(__fmul_rn(a0, c4.x), __fmul_rn(-a1, s4v.x));
+        r[i + 1] = __fadd_rn(__fmul_rn(a1, c4.y), __fmul_rn(a0, s4v.y));
+        r[i + 2] = __fadd_rn(__fmul_rn(a2, c4.z), __fmul_rn(-a3, s4v.z));
+        r[i + 3] = __fadd_rn(__fmul_rn(a3, c4.w), __fmul_rn(a2, s4v.w));
+      }
+    }
+  }
+  uint4* cp = reinterpret_cast<uint4*>(p.C + row * p.ldc + col0);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    uint4 o;
+    o.x = pack_bf16x2(r[j * 8 + 0], r[j * 8 + 1]);
+    o.y = pack_bf16x2(r[j * 8 + 2], r[j * 8 + 3]);
+    o.z = pack_bf16x2(r[j * 8 + 4], r[j * 8 + 5]);
+    o.w = pack_bf16x2(r[j * 8 + 6], r[j * 8 + 7]);
+    cp[j] = o;
   }
 }
 

@@ -55,13 +55,15 @@ class CogVideoXDPMScheduler:
     def get_velocity(self, sample, noise, timesteps):
         """sqrt(ab)*noise - sqrt(1-ab)*sample, bf16 with the reference's rounding points."""
         a, b = self.coefficients(self._t(timesteps), sample.dtype)
+        sample, noise = sample.contiguous(), noise.contiguous()      # the reference passes permuted views (ref :446)
         out = torch.empty_like(sample)
-        L.velocity(sample.contiguous(), noise.contiguous(), out, a, b)
+        L.velocity(sample, noise, out, a, b)
         return out
 
     def add_noise(self, original_samples, noise, timesteps):
         """sqrt(ab)*x + sqrt(1-ab)*noise (only reached with --noise_step != 0, default 0)."""
         a, b = self.coefficients(self._t(timesteps), original_samples.dtype)
+        original_samples, noise = original_samples.contiguous(), noise.contiguous()
         out = torch.empty_like(original_samples)
-        L.velocity(noise.contiguous(), original_samples.contiguous(), out, a, -b)
+        L.velocity(noise, original_samples, out, a, -b)
         return out

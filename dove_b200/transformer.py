@@ -5,9 +5,10 @@ Mirror of the diffusers `CogVideoXTransformer3DModel` call surface the reference
 
 Token layout in HBM: ONE residual-stream buffer x [N, D] bf16 with the 226 text tokens first and the
 T/2*h/2*w/2 video tokens after them (the reference keeps two tensors and concatenates them 3x per block; all
-ops are row-wise so a single buffer with a `split_row` is equivalent).  Per block (7 kernel launches):
-  layernorm_mod (LN + AdaLN-Zero modulate, text/video segments)  -> fused QKV GEMM [N, 3D] (tcgen05)
-  -> qk_norm_rope (per-head LayerNorm + 3-D RoPE, in place)       -> attention (tcgen05 flash attention)
+ops are row-wise so a single buffer with a `split_row` is equivalent).  Per block (6 kernel launches):
+  layernorm_mod (LN + AdaLN-Zero modulate, text/video segments)
+  -> fused QKV GEMM [N, 3D] (tcgen05) with per-head q/k LayerNorm + 3-D RoPE in its epilogue
+  -> attention (tcgen05 flash attention)
   -> out-proj GEMM with gate*y + residual epilogue                -> layernorm_mod
   -> FF1 GEMM with GELU-tanh epilogue -> FF2 GEMM with gate*y + residual epilogue.
 The timestep is the constant 399 in DOVE (ref: :459-464), so the timestep embedding and all 42x2 modulation
@@ -48,6 +49,7 @@ class CogVideoXTransformer3DModel:
         if self.dim % 256 != 0:
             raise NotImplementedError("inner dim must be a multiple of 256")
         self._mods = {}
+        self.fuse_qk_norm_rope = True      # False: separate dove_qk_norm_rope_bf16 pass (kept for A/B tests)
         self._build(state_dict)
 
     @property
@@ -171,10 +173,15 @@ class CogVideoXTransformer3DModel:
         att = torch.empty(N, D, dtype=BF, device=dev)
         ff = torch.empty(N, c.ff_mult * D, dtype=BF, device=dev)
         scale = 1.0 / math.sqrt(c.attention_head_dim)
+        fuse_qk = self.fuse_qk_norm_rope and D % 256 == 0
         for b, (m1, m2) in zip(self.blocks, mods):
             L.layernorm_mod(x, n1, b.ln1[0], b.ln1[1], c.norm_eps, m1[4], m1[3], m1[1], m1[0], nt)
-            L.gemm(n1, b.wqkv, qkv, b.bqkv)
-            L.qk_norm_rope(qkv, H, b.qn[0], b.qn[1], b.kn[0], b.kn[1], 1e-6, cos, sin, nt if rope is not None else N)
+            if fuse_qk:     # QKV projection with per-head q/k LayerNorm + RoPE in the GEMM epilogue
+                L.gemm_qkv_norm_rope(n1, b.wqkv, qkv, b.bqkv, H, b.qn[0], b.qn[1], b.kn[0], b.kn[1], 1e-6, cos, sin,
+                                     nt if rope is not None else N)
+            else:
+                L.gemm(n1, b.wqkv, qkv, b.bqkv)
+                L.qk_norm_rope(qkv, H, b.qn[0], b.qn[1], b.kn[0], b.kn[1], 1e-6, cos, sin, nt if rope is not None else N)
             L.attention(qkv, att, H, scale)
             L.gemm(att, b.wo, x, b.bo, L.EPI_GATED_RES, aux=x, gate0=m1[5], gate1=m1[2], split_row=nt)
             L.layernorm_mod(x, n1, b.ln2[0], b.ln2[1], c.norm_eps, m2[4], m2[3], m2[1], m2[0], nt)

@@ -283,7 +283,9 @@ class AutoencoderKLCogVideoX:
     def frame_batches(num_frames, bs):
         nb = max(num_frames // bs, 1)
         rem = num_frames % bs
-        return [(bs * i + (0 if i == 0 else rem), bs * (i + 1) + rem) for i in range(nb)]
+        # diffusers slices x[:, :, start:end]; for clips shorter than one batch (e.g. the per-frame path, F = 1) the
+        # nominal end bs + rem overshoots and the slice clamps it
+        return [(bs * i + (0 if i == 0 else rem), min(bs * (i + 1) + rem, num_frames)) for i in range(nb)]
 
     @classmethod
     def latent_frames(cls, num_frames, bs=8, levels=2):

@@ -20,7 +20,7 @@ def _up_t(t):
 
 def frame_batches(n, bs):
     nb, rem = max(n // bs, 1), n % bs
-    return [(bs * i + (0 if i == 0 else rem), bs * (i + 1) + rem) for i in range(nb)]
+    return [(bs * i + (0 if i == 0 else rem), min(bs * (i + 1) + rem, n)) for i in range(nb)]
 
 
 def vae_encoder_macs(F, H, W, cfg=None):

@@ -39,6 +39,7 @@ extern "C" {
 #define DOVE_EPI_GELU_TANH 1   /* out = bf16(gelu_tanh(r))                  (FeedForward net.0, GELU-tanh)  */
 #define DOVE_EPI_GATED_RES 2   /* out = bf16(aux + bf16(gate[seg(m)][n]*r)) (CogVideoXBlock gated residual) */
 #define DOVE_EPI_ADD 3         /* out = bf16(r + aux)                       (ResnetBlock3D shortcut add)    */
+#define DOVE_EPI_QKV_NORM_ROPE 4 /* internal to dove_gemm_qkv_norm_rope_bf16: per-head q/k LayerNorm + RoPE      */
 
 int dove_abi_version(void);
 /* Idempotent: selects the device's attributes (SM count, opt-in shared memory), resolves the driver's
@@ -83,6 +84,15 @@ int dove_layernorm_mod_bf16(const void* x, void* out, int rows, int D, const voi
 int dove_qk_norm_rope_bf16(void* qkv, int rows, int heads, const void* q_w, const void* q_b, const void* k_w,
                            const void* k_b, float eps, const float* cos, const float* sin, int text_len,
                            void* stream);
+
+/* qkv[M, 3*heads*64] = [to_q | to_k | to_v](A) with the per-head LayerNorm(64, eps) on q and k and the 3-D RoPE
+ * (rows >= text_len) applied in the GEMM epilogue: dove_gemm_bf16 + dove_qk_norm_rope_bf16 in ONE kernel (one head =
+ * 64 accumulator columns held by one thread).  W: [3*heads*64, ldw] = cat(to_q, to_k, to_v weights), bias likewise;
+ * heads*64 % 256 == 0.  CogVideoXAttnProcessor2_0 up to (excluding) F.scaled_dot_product_attention. */
+int dove_gemm_qkv_norm_rope_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M,
+                                 int heads, int K, const void* bias, const void* q_w, const void* q_b,
+                                 const void* k_w, const void* k_b, float eps, const float* cos, const float* sin,
+                                 int text_len, void* stream);
 
 /* out[rows, heads*64] = softmax(q k^T * scale) v per head, non-causal, no mask.  q,k,v read from the fused
  * qkv [rows, 3*heads*64] buffer.  tcgen05 flash-attention kernel (S, P and O in TMEM, lazy rescaling).

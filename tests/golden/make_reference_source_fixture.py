@@ -9,6 +9,9 @@ exists; the GPU box only sees the committed outputs):
                                    pre-computed T5 embedding of "" ([226, 4096] bf16) that the reference feeds to every
                                    unit (ref :580-590, :423-428) — the only numeric fixture the reference ships.
 
+  cli_flags.json                   every `parser.add_argument` of the reference's __main__ (:507-554): flag, type, default,
+                                   nargs, action — the contract `dove_b200.cli.build_parser()` is tested against.
+
 Test fixtures only: nothing under dove_b200/ reads them.
 """
 import ast
@@ -21,9 +24,25 @@ HERE = Path(__file__).resolve().parent
 WANTED = ("no_grad", "prepare_rotary_positional_embeddings", "process_video")
 
 
+def cli_flags(tree):
+    flags = []
+    for node in ast.walk(tree):
+        if isinstance(node, ast.Call) and getattr(node.func, "attr", "") == "add_argument" \
+                and getattr(node.func.value, "id", "") == "parser":
+            kw = {}
+            for k in node.keywords:
+                if k.arg == "help":
+                    continue
+                kw[k.arg] = k.value.id if isinstance(k.value, ast.Name) else ast.literal_eval(k.value)
+            flags.append({"flag": ast.literal_eval(node.args[0]), **kw})
+    return flags
+
+
 def main():
     src = (REF / "inference_script.py").read_text()
     tree = ast.parse(src)
+    import json
+    (HERE / "cli_flags.json").write_text(json.dumps(cli_flags(tree), indent=1) + "\n")
     chunks = []
     for node in tree.body:
         if isinstance(node, ast.FunctionDef) and node.name in WANTED:

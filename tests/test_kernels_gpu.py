@@ -247,6 +247,47 @@ def test_qk_norm_rope(L):
     assert torch.equal(qkv[:, 2 * heads * 64:].float(), ref[:, 2 * heads * 64:])   # v untouched
 
 
+@pytest.mark.parametrize("rows,heads,text", [(300, 4, 10), (2600, 4, 230), (1000, 8, 1000)])
+def test_gemm_qkv_norm_rope_fused(L, rows, heads, text):
+    """QKV projection with the per-head q/k LayerNorm + RoPE in the GEMM epilogue (one kernel) against the fp32
+    arithmetic of Linear -> LayerNorm(64) -> apply_rotary_emb, and against the two-kernel path it replaces."""
+    from dove_b200.embeddings import get_3d_rotary_pos_embed
+    D = heads * 64
+    nv = rows - text
+    cos = sin = None
+    if nv > 0:
+        T, h = 2, 5
+        w_ = nv // (T * h)
+        assert T * h * w_ == nv
+        cos, sin = get_3d_rotary_pos_embed(64, None, (h, w_), T, grid_type="slice", max_size=(h, w_), device="cuda")
+        cos, sin = cos.contiguous(), sin.contiguous()
+    a = randn(rows, D, seed=1)
+    w = randn(3 * D, D, std=D ** -0.5, seed=2)
+    bias = randn(3 * D, std=0.1, seed=3)
+    ws = [randn(64, seed=4), randn(64, std=0.1, seed=5), randn(64, seed=6), randn(64, std=0.1, seed=7)]
+    fused = torch.full((rows, 3 * D), float("nan"), device="cuda", dtype=torch.bfloat16)
+    L.gemm_qkv_norm_rope(a, w, fused, bias, heads, *ws, 1e-6, cos, sin, text)
+    two = torch.empty_like(fused)
+    L.gemm(a, w, two, bias)
+    L.qk_norm_rope(two, heads, *ws, 1e-6, cos, sin, text)
+    torch.cuda.synchronize()
+    ref = rb(a.float() @ w.float().t() + bias.float())
+    for i in range(2):
+        t = ref[:, i * D:(i + 1) * D].reshape(rows, heads, 64)
+        t = rb(F.layer_norm(t, (64,), ws[2 * i].float(), ws[2 * i + 1].float(), 1e-6))
+        if nv > 0:
+            tv = t[text:]
+            xr, xi = tv.reshape(nv, heads, 32, 2).unbind(-1)
+            rot = torch.stack([-xi, xr], dim=-1).flatten(2)
+            t[text:] = tv * cos[:, None] + rot * sin[:, None]
+        ref[:, i * D:(i + 1) * D] = t.reshape(rows, D)
+    assert torch.isfinite(fused.float()).all()
+    e, e2 = rel_l2(fused, rb(ref)), rel_l2(fused, two)
+    print(f"gemm_qkv_norm_rope rows{rows} heads{heads}: vs fp32 {e:.3e}, vs two-kernel path {e2:.3e}")
+    assert e < TOL and e2 < TOL
+    assert torch.equal(fused[:, 2 * D:], two[:, 2 * D:])          # v columns: plain Linear, identical
+
+
 def test_gemv(L):
     N, K = 1000, 512
     x, w, b = randn(K, seed=1), randn(N, K, std=K ** -0.5, seed=2), randn(N, std=0.1, seed=3)
