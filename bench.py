@@ -159,7 +159,7 @@ def peaks():
 
 # ------------------------------------------------------------------------------------------------ per-call timing
 FAMILY = {"dove_conv3d_causal_bf16": "conv", "dove_conv_cl_bf16": "conv", "dove_attention_bf16": "attn",
-          "dove_gemm_bf16": "gemm", "dove_gn_apply_bf16": "norm", "dove_gn_finalize": "norm", "dove_gn_stats_bf16": "norm",
+          "dove_gemm_bf16": "gemm", "dove_gemm_qkv_norm_rope_bf16": "gemm", "dove_gn_apply_bf16": "norm", "dove_gn_finalize": "norm", "dove_gn_stats_bf16": "norm",
           "dove_layernorm_mod_bf16": "norm", "dove_qk_norm_rope_bf16": "norm"}
 
 
@@ -206,6 +206,10 @@ class CallTimer:
         if name == "dove_gemm_bf16":
             M, N, K = (_v(a[i]) for i in (6, 7, 8))
             return 2.0 * M * N * K, ("gemm", M, N, K), 2.0 * (M * K + N * K + M * N)
+        if name == "dove_gemm_qkv_norm_rope_bf16":
+            M, heads, K = (_v(a[i]) for i in (6, 7, 8))
+            N = 3 * heads * 64
+            return 2.0 * M * N * K, ("gemm+qk_norm_rope", M, N, K), 2.0 * (M * K + N * K + M * N)
         if name == "dove_attention_bf16":
             rows, heads = _v(a[2]), _v(a[3])
             return 4.0 * rows * rows * heads * 64, ("attn", rows, heads), 2.0 * 4 * rows * heads * 64
@@ -559,6 +563,12 @@ def main():
         line["top_classes"] = [{"class": " ".join(str(x) for x in k), "launches_per_step": v[0] / args.steps,
                                 "ms_per_step": v[1] / args.steps,
                                 "tflops": (v[2] / (v[1] / 1e3) / 1e12) if v[2] else None} for k, v in top]
+        dump = os.environ.get("DOVE_BENCH_CLASSES")          # full per-class table (every conv / gemm / attn shape) to a file
+        if dump:
+            rows = [{"class": " ".join(str(x) for x in k), "launches_per_step": v[0] / args.steps, "ms_per_step": v[1] / args.steps,
+                     "tflops": (v[2] / (v[1] / 1e3) / 1e12) if v[2] and v[1] > 0 else None}
+                    for k, v in sorted(classes.items(), key=lambda kv: -kv[1][1])]
+            Path(dump).write_text(json.dumps(rows, indent=1))
         if per_rank:
             line["ranks"] = per_rank
         if cfg1:

@@ -177,16 +177,25 @@ def qk_norm_rope(qkv, heads, q_w, q_b, k_w, k_b, eps, cos, sin, text_len):
     return qkv
 
 
-def gemm_qkv_norm_rope(a, w, out, bias, heads, q_w, q_b, k_w, k_b, eps, cos, sin, text_len):
-    """out[M, 3*heads*64] = qkv projection with per-head q/k LayerNorm + RoPE fused in the GEMM epilogue."""
+def rope_tables_transposed(cos, sin):
+    """[nv, 64] pair-duplicated RoPE tables -> ([32, nv], [32, nv]) fp32 contiguous, the layout of the fused QKV epilogue.
+    Raises if the tables are not pair-duplicated (get_3d_rotary_pos_embed repeats every frequency twice)."""
+    if not (torch.equal(cos[:, 0::2], cos[:, 1::2]) and torch.equal(sin[:, 0::2], sin[:, 1::2])):
+        raise DoveError("fused QKV epilogue needs pair-duplicated RoPE tables (interleaved real layout)")
+    return cos[:, 0::2].t().contiguous(), sin[:, 0::2].t().contiguous()
+
+
+def gemm_qkv_norm_rope(a, w, out, bias, heads, q_w, q_b, k_w, k_b, eps, cos_t, sin_t, text_len):
+    """out[M, 3*heads*64] = qkv projection with per-head q/k LayerNorm + RoPE fused in the GEMM epilogue.
+    cos_t / sin_t: `rope_tables_transposed(cos, sin)` ([32, M - text_len] fp32) or None when no row is rotated."""
     M, K = a.shape
     assert a.dtype == w.dtype == out.dtype == torch.bfloat16 and a.stride(1) == 1 and out.stride(1) == 1
     assert tuple(w.shape) == (3 * heads * 64, K) and tuple(out.shape) == (M, 3 * heads * 64)
-    if cos is not None:
-        assert cos.dtype == torch.float32 and cos.is_contiguous() and cos.shape == (M - text_len, 64)
-        assert sin.dtype == torch.float32 and sin.is_contiguous() and sin.shape == cos.shape
+    if cos_t is not None:
+        assert cos_t.dtype == torch.float32 and cos_t.is_contiguous() and cos_t.shape == (32, M - text_len)
+        assert sin_t.dtype == torch.float32 and sin_t.is_contiguous() and sin_t.shape == cos_t.shape
     _call("dove_gemm_qkv_norm_rope_bf16", _p(a), a.stride(0), _p(w), w.stride(0), _p(out), out.stride(0), M, heads, K,
-          _p(_bf16c(bias)), _p(q_w), _p(q_b), _p(k_w), _p(k_b), eps, _p(cos), _p(sin), text_len, _stream())
+          _p(_bf16c(bias)), _p(q_w), _p(q_b), _p(k_w), _p(k_b), eps, _p(cos_t), _p(sin_t), text_len, _stream())
     return out
 
 

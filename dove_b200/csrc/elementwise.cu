@@ -414,8 +414,9 @@ __global__ void __launch_bounds__(256) gn_apply_spatial_kernel(const bf16* __res
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           __nv_bfloat162 n2 = __floats2bfloat162_rn(f[2 * k] * a[2 * k] + b[2 * k], f[2 * k + 1] * a[2 * k + 1] + b[2 * k + 1]);
-          n2 = __hadd2(__hmul2(n2, *reinterpret_cast<const __nv_bfloat162*>(&yw[k])),
-                       *reinterpret_cast<const __nv_bfloat162*>(&bw[k]));
+          // _rn variants: never contracted into one fma (the reference rounds the product to bf16 before the add)
+          n2 = __hadd2_rn(__hmul2_rn(n2, *reinterpret_cast<const __nv_bfloat162*>(&yw[k])),
+                          *reinterpret_cast<const __nv_bfloat162*>(&bw[k]));
           if (apply_silu) {
             const float2 v2 = __bfloat1622float2(n2);
             n2 = __floats2bfloat162_rn(silu_fast(v2.x), silu_fast(v2.y));

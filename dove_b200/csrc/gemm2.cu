@@ -18,7 +18,9 @@ struct Gemm2Cfg {
   static constexpr size_t SMEM = 1024 + STAGES * (A_BYTES + B_BYTES) + 256;
 };
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
+// 320 threads: __launch_bounds__(320, 1) makes ptxas budget registers for 384 threads (168 per thread) and the fused QKV
+// epilogue spills; __maxnreg__(200) states the real limit (10 warps x 32 x 200 = 64 000 <= 65 536 registers).
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(200)
 gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const GemmParams p) {
   using Cfg = Gemm2Cfg;
@@ -181,8 +183,8 @@ int gemm2cta_launch(const void* A, long long lda, const void* W, long long ldw, 
 // (dove_qk_norm_rope_bf16) disappears from the DiT block.
 extern "C" int dove_gemm_qkv_norm_rope_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc,
                                             int M, int heads, int K, const void* bias, const void* q_w, const void* q_b,
-                                            const void* k_w, const void* k_b, float eps, const float* cos,
-                                            const float* sin, int text_len, void* stream) {
+                                            const void* k_w, const void* k_b, float eps, const float* cos_t,
+                                            const float* sin_t, int text_len, void* stream) {
   using namespace dove;
   if (int e = ensure_init()) return e;
   const int N = 3 * heads * 64;
@@ -192,7 +194,7 @@ extern "C" int dove_gemm_qkv_norm_rope_bf16(const void* A, int64_t lda, const vo
   DOVE_CHECK_ARG((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(C)) % 16 == 0,
                  "gemm_qkv: pointers must be 16-byte aligned");
   DOVE_CHECK_ARG(bias && q_w && q_b && k_w && k_b, "gemm_qkv: bias and norm_q / norm_k parameters required");
-  DOVE_CHECK_ARG(text_len >= M || (cos && sin), "gemm_qkv: cos/sin tables required");
+  DOVE_CHECK_ARG(text_len >= M || (cos_t && sin_t), "gemm_qkv: cos/sin tables required");
   GemmParams p{};
   p.M = M;
   p.epi = DOVE_EPI_QKV_NORM_ROPE;
@@ -205,8 +207,9 @@ extern "C" int dove_gemm_qkv_norm_rope_bf16(const void* A, int64_t lda, const vo
   p.qk_b[0] = static_cast<const bf16*>(q_b);
   p.qk_w[1] = static_cast<const bf16*>(k_w);
   p.qk_b[1] = static_cast<const bf16*>(k_b);
-  p.rope_cos = cos;
-  p.rope_sin = sin;
+  p.rope_cos = cos_t;
+  p.rope_sin = sin_t;
+  p.rope_ld = M - text_len;
   p.text_len = text_len;
   p.heads = heads;
   p.qk_eps = eps;

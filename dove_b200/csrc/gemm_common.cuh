@@ -33,8 +33,9 @@ struct GemmParams {
   // DOVE_EPI_QKV_NORM_ROPE (dense CTA-pair GEMM only): per-head LayerNorm(64) on the q / k column blocks + 3-D RoPE
   const bf16* qk_w[2];   // norm_q.weight, norm_k.weight  [64]
   const bf16* qk_b[2];   // norm_q.bias,   norm_k.bias    [64]
-  const float* rope_cos; // [rows - text_len, 64] fp32 (may be null when text_len >= rows)
+  const float* rope_cos; // TRANSPOSED, pair-deduplicated tables [32][rope_ld] fp32 (null when text_len >= rows)
   const float* rope_sin;
+  long long rope_ld;     // = rows - text_len
   int text_len, heads;
   float qk_eps;
   // fused GroupNorm statistics of the OUTPUT (consumed by the next GroupNorm): per-CTA partial sums
@@ -222,30 +223,41 @@ __device__ __forceinline__ void qkv_head_epilogue(const GemmParams& p, const uin
         r[i + 1] = bf16_round(r[i + 1] * rstd * w2.y + b2.y);
       }
     }
-    if (row >= p.text_len) {      // out = x*cos + rot(x)*sin, rot(x)[2i] = -x[2i+1], rot(x)[2i+1] = x[2i]  (no fma)
-      const float4* cp = reinterpret_cast<const float4*>(p.rope_cos + (row - p.text_len) * 64);
-      const float4* sp = reinterpret_cast<const float4*>(p.rope_sin + (row - p.text_len) * 64);
+  }
+  // RoPE (rows >= text_len of q / k heads) fused with the store, 8 pairs at a time.  The tables arrive TRANSPOSED and
+  // pair-deduplicated, [32][nv] fp32 (cos[i][token] = cos_table[token][2i] = cos_table[token][2i+1]), so that the 32
+  // lanes of a warp (32 consecutive rows) read 128 contiguous bytes per column instead of 32 rows 256 B apart.
+  const bool rope = which < 2 && row >= p.text_len;
+  const float* cp = p.rope_cos + (row - p.text_len);
+  const float* sp = p.rope_sin + (row - p.text_len);
+  uint4* op = reinterpret_cast<uint4*>(p.C + row * p.ldc + col0);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float4 c4 = cp[j], s4v = sp[j];
-        const int i = j * 4;
-        const float a0 = r[i], a1 = r[i + 1], a2 = r[i + 2], a3 = r[i + 3];
-        r[i] = __fadd_rn(__fmul_rn(a0, c4.x), __fmul_rn(-a1, s4v.x));
-        r[i + 1] = __fadd_rn(__fmul_rn(a1, c4.y), __fmul_rn(a0, s4v.y));
-        r[i + 2] = __fadd_rn(__fmul_rn(a2, c4.z), __fmul_rn(-a3, s4v.z));
-        r[i + 3] = __fadd_rn(__fmul_rn(a3, c4.w), __fmul_rn(a2, s4v.w));
+  for (int g = 0; g < 4; ++g) {
+    if (rope) {      // out = x*cos + rot(x)*sin, rot(x)[2i] = -x[2i+1], rot(x)[2i+1] = x[2i]  (fp32, no fma)
+      float c[8], sn[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        c[k] = cp[static_cast<long long>(g * 8 + k) * p.rope_ld];
+        sn[k] = sp[static_cast<long long>(g * 8 + k) * p.rope_ld];
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int i = g * 16 + 2 * k;
+        const float a0 = r[i], a1 = r[i + 1];
+        r[i] = __fadd_rn(__fmul_rn(a0, c[k]), __fmul_rn(-a1, sn[k]));
+        r[i + 1] = __fadd_rn(__fmul_rn(a1, c[k]), __fmul_rn(a0, sn[k]));
       }
     }
-  }
-  uint4* cp = reinterpret_cast<uint4*>(p.C + row * p.ldc + col0);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    uint4 o;
-    o.x = pack_bf16x2(r[j * 8 + 0], r[j * 8 + 1]);
-    o.y = pack_bf16x2(r[j * 8 + 2], r[j * 8 + 3]);
-    o.z = pack_bf16x2(r[j * 8 + 4], r[j * 8 + 5]);
-    o.w = pack_bf16x2(r[j * 8 + 6], r[j * 8 + 7]);
-    cp[j] = o;
+    for (int h2 = 0; h2 < 2; ++h2) {
+      const int i = g * 16 + h2 * 8;
+      uint4 o;
+      o.x = pack_bf16x2(r[i + 0], r[i + 1]);
+      o.y = pack_bf16x2(r[i + 2], r[i + 3]);
+      o.z = pack_bf16x2(r[i + 4], r[i + 5]);
+      o.w = pack_bf16x2(r[i + 6], r[i + 7]);
+      op[g * 2 + h2] = o;
+    }
   }
 }
 

@@ -141,7 +141,9 @@ class CogVideoXPipeline:
             latent[:ncopy] = z[:, :1].permute(1, 0, 2, 3)
         Fl = latent.shape[0]
         if noise_step != 0:                                                             # ref :449-457
-            n = torch.randn(latent.shape, device=dev, dtype=latent.dtype, generator=generator)
+            # the reference draws randn_like(latent) on the PERMUTED view of the [B,C,F,H,W] tensor (ref :446, :451), i.e.
+            # in (C, F, h, w) memory order: draw in that order, then view it frame-major like `latent`
+            n = torch.randn((16, Fl, h, w), device=dev, dtype=latent.dtype, generator=generator).permute(1, 0, 2, 3)
             latent = self.scheduler.add_noise(latent, n, torch.tensor([noise_step]))
         emb = self._prompt_on_device(empty_prompt_embedding)                            # ref :423-428
         tc = self.transformer.config

@@ -49,6 +49,7 @@ class CogVideoXTransformer3DModel:
         if self.dim % 256 != 0:
             raise NotImplementedError("inner dim must be a multiple of 256")
         self._mods = {}
+        self._rope_t = None
         self.fuse_qk_norm_rope = True      # False: separate dove_qk_norm_rope_bf16 pass (kept for A/B tests)
         self._build(state_dict)
 
@@ -174,10 +175,16 @@ class CogVideoXTransformer3DModel:
         ff = torch.empty(N, c.ff_mult * D, dtype=BF, device=dev)
         scale = 1.0 / math.sqrt(c.attention_head_dim)
         fuse_qk = self.fuse_qk_norm_rope and D % 256 == 0
+        cos_t = sin_t = None
+        if fuse_qk and rope is not None:       # transposed tables of the fused epilogue, cached per table object
+            key = (cos.data_ptr(), tuple(cos.shape))
+            if self._rope_t is None or self._rope_t[0] != key:
+                self._rope_t = (key, cos, L.rope_tables_transposed(cos, sin))
+            cos_t, sin_t = self._rope_t[2]
         for b, (m1, m2) in zip(self.blocks, mods):
             L.layernorm_mod(x, n1, b.ln1[0], b.ln1[1], c.norm_eps, m1[4], m1[3], m1[1], m1[0], nt)
             if fuse_qk:     # QKV projection with per-head q/k LayerNorm + RoPE in the GEMM epilogue
-                L.gemm_qkv_norm_rope(n1, b.wqkv, qkv, b.bqkv, H, b.qn[0], b.qn[1], b.kn[0], b.kn[1], 1e-6, cos, sin,
+                L.gemm_qkv_norm_rope(n1, b.wqkv, qkv, b.bqkv, H, b.qn[0], b.qn[1], b.kn[0], b.kn[1], 1e-6, cos_t, sin_t,
                                      nt if rope is not None else N)
             else:
                 L.gemm(n1, b.wqkv, qkv, b.bqkv)

@@ -88,10 +88,12 @@ int dove_qk_norm_rope_bf16(void* qkv, int rows, int heads, const void* q_w, cons
 /* qkv[M, 3*heads*64] = [to_q | to_k | to_v](A) with the per-head LayerNorm(64, eps) on q and k and the 3-D RoPE
  * (rows >= text_len) applied in the GEMM epilogue: dove_gemm_bf16 + dove_qk_norm_rope_bf16 in ONE kernel (one head =
  * 64 accumulator columns held by one thread).  W: [3*heads*64, ldw] = cat(to_q, to_k, to_v weights), bias likewise;
- * heads*64 % 256 == 0.  CogVideoXAttnProcessor2_0 up to (excluding) F.scaled_dot_product_attention. */
+ * heads*64 % 256 == 0.  cos_t / sin_t: the RoPE tables TRANSPOSED and pair-deduplicated, fp32 [32][M - text_len] with
+ * cos_t[i][token] = cos[token][2i] (= cos[token][2i+1]: get_3d_rotary_pos_embed repeats every frequency twice), so a
+ * warp's 32 rows read contiguous memory.  CogVideoXAttnProcessor2_0 up to (excluding) F.scaled_dot_product_attention. */
 int dove_gemm_qkv_norm_rope_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M,
                                  int heads, int K, const void* bias, const void* q_w, const void* q_b,
-                                 const void* k_w, const void* k_b, float eps, const float* cos, const float* sin,
+                                 const void* k_w, const void* k_b, float eps, const float* cos_t, const float* sin_t,
                                  int text_len, void* stream);
 
 /* out[rows, heads*64] = softmax(q k^T * scale) v per head, non-causal, no mask.  q,k,v read from the fused

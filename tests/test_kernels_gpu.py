@@ -266,7 +266,8 @@ def test_gemm_qkv_norm_rope_fused(L, rows, heads, text):
     bias = randn(3 * D, std=0.1, seed=3)
     ws = [randn(64, seed=4), randn(64, std=0.1, seed=5), randn(64, seed=6), randn(64, std=0.1, seed=7)]
     fused = torch.full((rows, 3 * D), float("nan"), device="cuda", dtype=torch.bfloat16)
-    L.gemm_qkv_norm_rope(a, w, fused, bias, heads, *ws, 1e-6, cos, sin, text)
+    ct, st = L.rope_tables_transposed(cos, sin) if nv > 0 else (None, None)
+    L.gemm_qkv_norm_rope(a, w, fused, bias, heads, *ws, 1e-6, ct, st, text)
     two = torch.empty_like(fused)
     L.gemm(a, w, two, bias)
     L.qk_norm_rope(two, heads, *ws, 1e-6, cos, sin, text)
