@@ -601,10 +601,19 @@ attn_fwd_v3_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
   }
 }
 
-// variant: 0 = v2 (2 CTAs/SM, one query tile each); 1 + e = v3 with e/8 of the exponentials on the FMA pipe
-static std::atomic<int> g_attn_variant{3};
+// Measured dead ends on B200 (round 2, N = 19 426, 48 heads; v3 with 1/8 emulation = 5.23-5.44 ms):
+//   * 64-key tiles with double-buffered S and P in TMEM (so that S(j+1) is always ready): 6.9-7.0 ms — every per-tile
+//     fixed cost (mbarrier hand-offs, tcgen05.wait::st, fences) doubles and the N = 64 QK^T MMA is shared-memory bound;
+//   * holding the whole S row (128 fp32) in registers and releasing the S buffer before the exponentials (early issue
+//     of the next QK^T): 6.3-6.5 ms — 320-thread CTAs get 168 registers per thread (the SM allocates registers for 12
+//     warps; 200 registers fail to launch), the row + P chunk spill, and the TMEM-load / compute overlap is lost;
+//   * more than 1/8 of the exponentials on the FMA pipe: slower (ncu: XU 71 %, FMA pipe 30 %, issue slots 42 % busy, MUFU
+//     instructions stalled on the MIO queue — the kernel sits at the practical throughput of the special-function path).
+// variant: -1 = auto (v3 with 1/8 emulation for long sequences, v2 below 6 000 rows where its 2x finer CTA grain wins);
+// 0 = v2 (2 CTAs/SM, one query tile each); 1 + e (e = 0..5) = v3 with e/8 of the exponentials on the FMA pipe
+static std::atomic<int> g_attn_variant{-1};
 int set_attn_variant(int v) {
-  if (v < 0 || v > 6) return set_error(DOVE_E_BAD_ARG, "attn_variant must be 0..6");
+  if (v < -1 || v > 6) return set_error(DOVE_E_BAD_ARG, "attn_variant must be -1..6");
   g_attn_variant.store(v);
   return DOVE_OK;
 }
@@ -644,7 +653,8 @@ static int attention_launch(const void* qkv, void* out, int rows, int heads, flo
   p.nkv = (rows + 127) / 128;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.out = static_cast<bf16*>(out);
-  const int variant = g_attn_variant.load();
+  int variant = g_attn_variant.load();
+  if (variant < 0) variant = rows >= 6000 ? 2 : 0;
   switch (variant) {
     case 1: return launch_v3<0>(tm, p, st);
     case 2: return launch_v3<1>(tm, p, st);

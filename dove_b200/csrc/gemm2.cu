@@ -18,9 +18,9 @@ struct Gemm2Cfg {
   static constexpr size_t SMEM = 1024 + STAGES * (A_BYTES + B_BYTES) + 256;
 };
 
-// 320 threads: __launch_bounds__(320, 1) makes ptxas budget registers for 384 threads (168 per thread) and the fused QKV
-// epilogue spills; __maxnreg__(200) states the real limit (10 warps x 32 x 200 = 64 000 <= 65 536 registers).
-__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(200)
+// (320 threads get 168 registers each: the SM allocates registers for 12 warps — warps come in groups of four — so
+// 200 registers x 320 threads fails to launch with "too many resources"; measured on B200.)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const GemmParams p) {
   using Cfg = Gemm2Cfg;

@@ -49,8 +49,9 @@ const char* dove_last_error(void);
 int dove_num_sms(void);
 /* Tuning / test switches.  "conv2cta": 1 (default) = big stride-1 3x3(x3) convs on images >= 256 wide run on the
  * CTA-pair kernel (cta_group::2 MMA + in-smem reuse of the W taps), 0 = always the 1-CTA kernel (tests).
- * "attn_variant": 0 = one query tile per CTA, two CTAs per SM (round-1 kernel); 1 + e (e = 0..5) = two query tiles
- * per CTA sharing the K/V stages, with e/8 of the softmax exponentials evaluated on the FMA pipe (see attn.cu). */
+ * "attn_variant": -1 (default) = automatic; 0 = one query tile per CTA, two CTAs per SM (round-1 kernel, best below
+ * ~6 000 rows); 1 + e (e = 0..5) = two query tiles per CTA sharing the K/V stages, no row-max pass in the steady state,
+ * e/8 of the softmax exponentials evaluated on the FMA pipe (see attn.cu). */
 int dove_set_option(const char* name, int value);
 
 /* ---- DiT -------------------------------------------------------------------------------------------------- */
