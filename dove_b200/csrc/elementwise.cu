@@ -252,24 +252,33 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const bf16* __restrict_
   }
 }
 
-// one warp per group: lanes stride over the per-block partials (fixed order -> deterministic), fp64 combine
-__global__ void gn_finalize_kernel(const float* __restrict__ partial, int nblocks, int groups, double count,
-                                   float eps, float* __restrict__ stats) {
-  const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (g >= groups) return;
+// one 256-thread block per group: threads stride over the per-CTA partials, fp64 accumulation, fixed-order tree combine
+// (deterministic).  (Round 1 used one WARP per group in a single block: 37 dependent fp64 adds per lane, ~58 us per call x
+// 264 calls per clip.)
+__global__ void __launch_bounds__(256) gn_finalize_kernel(const float* __restrict__ partial, int nblocks, int groups,
+                                                          double count, float eps, float* __restrict__ stats) {
+  __shared__ double sh_s[256], sh_q[256];
+  const int g = blockIdx.x;
   double s = 0.0, q = 0.0;
-  for (int b = lane; b < nblocks; b += 32) {
-    s += partial[(static_cast<long long>(b) * groups + g) * 2];
-    q += partial[(static_cast<long long>(b) * groups + g) * 2 + 1];
+  for (int b = threadIdx.x; b < nblocks; b += 256) {
+    const float2 v = *reinterpret_cast<const float2*>(partial + (static_cast<long long>(b) * groups + g) * 2);
+    s += v.x;
+    q += v.y;
   }
+  sh_s[threadIdx.x] = s;
+  sh_q[threadIdx.x] = q;
+  __syncthreads();
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    s += __shfl_xor_sync(0xffffffffu, s, o);
-    q += __shfl_xor_sync(0xffffffffu, q, o);
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      sh_s[threadIdx.x] += sh_s[threadIdx.x + o];
+      sh_q[threadIdx.x] += sh_q[threadIdx.x + o];
+    }
+    __syncthreads();
   }
-  if (lane == 0) {
-    const double mean = s / count;
-    double var = q / count - mean * mean;
+  if (threadIdx.x == 0) {
+    const double mean = sh_s[0] / count;
+    double var = sh_q[0] / count - mean * mean;
     if (var < 0.0) var = 0.0;
     stats[g * 2] = static_cast<float>(mean);
     stats[g * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
@@ -692,7 +701,7 @@ extern "C" int dove_gn_stats_bf16(const void* x, int64_t nvox, int C, int groups
   gn_partial_kernel<<<static_cast<int>(blocks), 256, 0, ST(stream)>>>(static_cast<const bf16*>(x), nvox, C, groups,
                                                                     partial);
   DOVE_LAUNCH_CHECK("gn_partial_kernel");
-  gn_finalize_kernel<<<1, 32 * 32, 0, ST(stream)>>>(partial, static_cast<int>(blocks), groups,
+  gn_finalize_kernel<<<groups, 256, 0, ST(stream)>>>(partial, static_cast<int>(blocks), groups,
                                               static_cast<double>(nvox) * (C / groups), eps, stats);
   DOVE_LAUNCH_CHECK("gn_finalize_kernel");
   return DOVE_OK;
@@ -702,7 +711,7 @@ extern "C" int dove_gn_finalize(const float* partial, int64_t nvox, int C, int g
                                void* stream) {
   if (int e = ensure_init()) return e;
   DOVE_CHECK_ARG(groups == 32 && C % 32 == 0 && nvox > 0, "gn_finalize: bad shape");
-  gn_finalize_kernel<<<1, 32 * 32, 0, ST(stream)>>>(partial, GN_MAX_BLOCKS, groups,
+  gn_finalize_kernel<<<groups, 256, 0, ST(stream)>>>(partial, GN_MAX_BLOCKS, groups,
                                                    static_cast<double>(nvox) * (C / groups), eps, stats);
   DOVE_LAUNCH_CHECK("gn_finalize_kernel");
   return DOVE_OK;

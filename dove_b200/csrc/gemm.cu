@@ -17,6 +17,8 @@ namespace dove {
 
 int conv2cta_dispatch(const void* x, const void* x_prev, int Tin, const void* w, int Tout, int Hin, int Win, int Cin,
                       int Cout_pad, int kt, int Ho, int Wo, GemmParams p, cudaStream_t st);
+int conv_narrow_dispatch(const void* x, const void* x_prev, int Tin, const void* w, int Tout, int H, int W, int Cin,
+                         GemmParams p, cudaStream_t st);
 int get_option_conv2cta();
 int gemm2cta_launch(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K, GemmParams p,
                     cudaStream_t st);
@@ -53,8 +55,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
 
-  __shared__ float gn_red[8 * 64];                  // per-epilogue-warp GroupNorm partials (kTrans only)
-  if (kTrans)
+  __shared__ float gn_red[8 * 64];                  // per-epilogue-warp GroupNorm partials [warp][group][2] (convs)
+  if (kConv)
     for (int i = threadIdx.x; i < 8 * 64; i += blockDim.x) gn_red[i] = 0.f;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -238,7 +240,28 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (CH == 32) tmem_ld32(t_row + c0, v); else tmem_ld16(t_row + c0, v);
         tmem_ld_wait();
         const int n0 = nt * BN + c0;
-        if (valid) {
+        if (kConv && CH == 32 && p.gn_partial) {      // fused GroupNorm statistics of the output (as in conv2cta)
+          float qs[8], qss[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) qs[i] = qss[i] = 0.f;
+          if (valid) epilogue_chunk<CH, true>(p, v, row, n0, gate, qs, qss);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              qs[i] += __shfl_xor_sync(0xffffffffu, qs[i], o);
+              qss[i] += __shfl_xor_sync(0xffffffffu, qss[i], o);
+            }
+          }
+          if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int g = (n0 + 4 * i) / p.gn_cpg;
+              gn_red[(warp - 2) * 64 + g * 2] += qs[i];
+              gn_red[(warp - 2) * 64 + g * 2 + 1] += qss[i];
+            }
+          }
+        } else if (valid) {
           epilogue_chunk<CH>(p, v, row, n0, gate);
         }
       }
@@ -262,7 +285,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
-  if (kTrans && p.gn_partial && threadIdx.x < 64) {   // fixed-order combine of the 8 epilogue warps
+  if (kConv && p.gn_partial && threadIdx.x < 64) {    // fixed-order combine of the 8 epilogue warps
     float a8 = 0.f;
 #pragma unroll
     for (int w8 = 0; w8 < 8; ++w8) a8 += gn_red[w8 * 64 + threadIdx.x];
@@ -440,6 +463,30 @@ static int conv_impl(const void* x, const void* x_prev, int cached, const void* 
                                static_cast<cudaStream_t>(stream));
     }
   }
+  // narrow outputs (decoder conv_out, 128 -> 3): resident weights + (dh, dw) tap reuse out of one halo box (conv3.cu)
+  if (get_option_conv2cta() != 0 && Cout_pad == 16 && kt == 3 && kh == 3 && kw == 3 && stride == 1 && pad == 1 &&
+      Cin <= 128 && Wo >= 128 && Hin == Ho && Win == Wo && (epilogue == DOVE_EPI_BIAS || out_mode == 0)) {
+    GemmParams q{};
+    q.Ho = Ho;
+    q.Wo = Wo;
+    q.kh = kh;
+    q.kw = kw;
+    q.stride = 1;
+    q.pad = 1;
+    q.t_shift = t_shift;
+    q.has_prev = has_prev;
+    q.epi = epilogue;
+    q.C = static_cast<bf16*>(y);
+    q.ldc = ldy;
+    q.bias = static_cast<const bf16*>(bias);
+    q.aux = static_cast<const bf16*>(aux);
+    q.ld_aux = ld_aux;
+    q.n_valid = cout_valid;
+    q.out_mode = out_mode;
+    q.rows_total = out_mode >= 1 ? ldy : static_cast<long long>(Tout) * Ho * Wo;
+    return conv_narrow_dispatch(x, has_prev ? x_prev : nullptr, Tin_all, w, Tout, Hin, Win, Cin, q,
+                                static_cast<cudaStream_t>(stream));
+  }
   // 128-channel-out convs on large images: swapped operand roles (weights = M 128, voxels = N 256)
   const bool trans = get_option_conv2cta() != 0 && stride == 1 && out_mode == 0 && Cout_pad == 128 &&
                      cout_valid == 128 && static_cast<long long>(Ho) * Wo >= 4096;
@@ -587,6 +634,14 @@ static int conv_impl(const void* x, const void* x_prev, int cached, const void* 
   p.n_valid = cout_valid;
   p.out_mode = out_mode;
   p.rows_total = out_mode >= 1 ? ldy : static_cast<long long>(Tout) * Ho * Wo;
+  // fused GroupNorm statistics on the generic kernel too (32-column epilogue chunks, >= 4 channels per group)
+  if (gn_partial && gn_done && out_mode == 0 && bn >= 32 && cout_valid == Cout_pad && cout_valid % 128 == 0) {
+    if (int e = check_cuda(cudaMemsetAsync(gn_partial, 0, sizeof(float) * GN_PARTIAL_ROWS * 64,
+                                           static_cast<cudaStream_t>(stream)), "gn partial memset")) return e;
+    p.gn_partial = gn_partial;
+    p.gn_cpg = cout_valid / 32;
+    *gn_done = 1;
+  }
   return dispatch_bn<true>(bn, tmA, tmB, tmP, p, static_cast<cudaStream_t>(stream));
 }
 

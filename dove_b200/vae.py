@@ -271,8 +271,8 @@ class AutoencoderKLCogVideoX:
                     x, T = y, To
                 Ho, Wo = H // 2, W // 2
                 y = self._empty(T, Ho, Wo, C)
-                L.conv_cl(x, down.w, down.b, y, T, 1, 3, 3, 2, 0, Ho, Wo, down.cout)
-                x, H, W, st = y, Ho, Wo, False
+                _, st = L.conv_cl(x, down.w, down.b, y, T, 1, 3, 3, 2, 0, Ho, Wo, down.cout, gn_partial=self._partial)
+                x, H, W = y, Ho, Wo
         for r in self.enc_mid:
             x, st = self._resnet(r, x, T, H, W, None, cache, st)
         C = self.enc_conv_out.cin
