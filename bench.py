@@ -441,6 +441,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     L.init(local_rank)
+    if os.environ.get("DOVE_ATTN_VARIANT"):     # kernel A/B runs only (profiles/run_gpu_*.sh); default = automatic choice
+        L.set_option("attn_variant", int(os.environ["DOVE_ATTN_VARIANT"]))
     pipe = CogVideoXPipeline.from_random(seed=1234, device=dev, dit_config=dict(num_layers=args.layers))
     emb, emb_src = prompt_embedding()
     wl = WORKLOADS[args.workload]

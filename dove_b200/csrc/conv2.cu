@@ -75,7 +75,7 @@ conv2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one()) {
     // ===================== TMA producer (both CTAs) =====================
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
@@ -107,7 +107,7 @@ conv2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
       }
     }
-  } else if (warp == 1 && lane == 0 && rank == 0) {
+  } else if (warp == 1 && rank == 0 && elect_one()) {
     // ===================== MMA issuer (leader CTA, one thread) =====================
     constexpr uint32_t idesc = umma_idesc_bf16(256, BN, 0, 0);
     int sa = 0, sb = 0, acc = 0;

@@ -61,7 +61,7 @@ conv_narrow_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one()) {
     // ===================== TMA producer =====================
     mbar_expect_tx(b_full, static_cast<uint32_t>(num_kb) * Cfg::B_KB_BYTES);       // resident weights, loaded once
     for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(sB + kb * Cfg::B_KB_BYTES, &tmB, b_full, kb * 64, 0);
@@ -81,7 +81,7 @@ conv_narrow_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (++sa == SA) { sa = 0; pa ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1 && elect_one()) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = umma_idesc_bf16(128, 16, 0, 0);
     mbar_wait(b_full, 0);

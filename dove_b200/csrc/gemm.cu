@@ -81,7 +81,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one()) {
     // ===================== TMA producer =====================
     int stage = 0;
     uint32_t phase = 0;
@@ -118,7 +118,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1 && elect_one()) {
     // ===================== MMA issuer (one thread) =====================
     constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
     int stage = 0;

@@ -55,7 +55,7 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one()) {
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = pair; tile < total_tiles; tile += npairs) {
@@ -71,7 +71,7 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0 && rank == 0) {
+  } else if (warp == 1 && rank == 0 && elect_one()) {
     constexpr uint32_t idesc = umma_idesc_bf16(256, BN, 0, 0);
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;

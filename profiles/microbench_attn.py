@@ -14,7 +14,8 @@ from dove_b200 import _lib as L   # noqa: E402
 pk = os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")
 BURST = json.load(open(pk))["bf16_tflops"] if os.path.exists(pk) else 1590.0
 NAMES = {0: "v2 (1 Q tile/CTA, 2 CTAs/SM)", 1: "v3 emu 0/8", 2: "v3 emu 1/8", 3: "v3 emu 2/8", 4: "v3 emu 3/8",
-         5: "v3 emu 4/8", 6: "v3 emu 5/8"}
+         5: "v3 emu 4/8", 6: "v3 emu 5/8", 7: "v4 emu 0/8", 8: "v4 emu 1/8", 9: "v4 emu 2/8", 10: "v4 emu 3/8",
+         11: "v4 emu 4/8"}
 
 
 def timeit(fn, flush, iters=8, warm=3):
@@ -31,6 +32,9 @@ def timeit(fn, flush, iters=8, warm=3):
     return t[len(t) // 2]
 
 
+VARIANTS = [int(v) for v in sys.argv[1:]] or list(range(12))
+
+
 def main():
     L.init(0)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -43,7 +47,7 @@ def main():
         ref = (p @ v).transpose(0, 1).reshape(512, heads * 64)
         del q, k, v, p
         print(f"## N = {n}, {heads} heads (burst peak {BURST} TFLOP/s)")
-        for var in range(7):
+        for var in VARIANTS:
             L.set_option("attn_variant", var)
             out = torch.zeros(n, heads * 64, device="cuda", dtype=torch.bfloat16)
             ms = timeit(lambda: L.attention(qkv, out, heads, 0.125), flush)
