@@ -308,8 +308,10 @@ def build_oracle_pipe(layers, device, dtype, channels_last=False):
             owner, attr = name.rsplit(".", 1)
             getattr(mod.get_submodule(owner), attr).data.copy_(t.to(dtype).cpu())
     vae, dit = vae.to(device).eval(), dit.to(device).eval()
-    if channels_last:
-        vae = vae.to(memory_format=torch.channels_last_3d)
+    if channels_last:       # only rank-5 tensors have a channels_last_3d format: convert the Conv3d weights one by one
+        for m in vae.modules():
+            if isinstance(m, torch.nn.Conv3d):
+                m.weight.data = m.weight.data.contiguous(memory_format=torch.channels_last_3d)
     return OraclePipe(vae, dit)
 
 
