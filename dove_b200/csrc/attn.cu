@@ -989,312 +989,31 @@ attn_fwd_v4_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
   }
 }
 
-// =====================================================================================================================
-// v5: v4's pipeline with SIXTEEN softmax warps (4 per SM sub-partition instead of 2).  ncu on v4: a softmax warp has a
-// MUFU.EX2 pending only ~46 % of its time (the rest is packing, row sums, TMEM traffic, hand-offs), so two warps per
-// sub-partition keep the 16-lane special-function unit ~73 % busy.  v5 splits every query row between TWO threads:
-// warps 4+8t+{0..3} take key columns 0..63 of query tile t, warps 4+8t+{4..7} columns 64..127 (a warp may touch the TMEM
-// lane quarter warp % 4, any column).  Consequences:
-//   * the two halves of a row must use ONE exponent reference, so every tile starts with the half-row maximum
-//     (32 FMNMX3), exchanged with the partner warp through shared memory + a 64-thread named barrier; with the true row
-//     maximum known up front the classic lazy rescale (only when it grew by > 8) replaces v3/v4's overflow detection and
-//     "exact path", and the S registers are dead as soon as they are exponentiated;
-//   * 640 threads: 96 registers at launch, setmaxnreg 40 (TMA / MMA warpgroup) / 104 (softmax);
-//   * S is released as soon as the half row is in registers (~200 clk into the tile), P is stored in two 32-key pieces,
-//     the first one only after PV_t(j-1) has retired; O rescale and the final normalisation are split by head-dim halves.
-constexpr size_t A5_SMEM = A4_SMEM + 2 * 2 * 128 * sizeof(float);
-
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-template <int EMU8>
-__global__ void __launch_bounds__(640, 1)
-attn_fwd_v5_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                                   // 2 query tiles
-  uint8_t* sK = sQ + 2 * ATT_TILE_BYTES;
-  uint8_t* sV = sK + A4_KS * ATT_TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + A4_VS * ATT_TILE_BYTES);
-  uint64_t* q_full = bars;
-  uint64_t* k_full = bars + 1;
-  uint64_t* k_empty = k_full + A4_KS;
-  uint64_t* v_full = k_empty + A4_KS;
-  uint64_t* v_empty = v_full + A4_VS;
-  uint64_t* s_full = v_empty + A4_VS;                   // [2]
-  uint64_t* s_free = s_full + 2;                        // [2]  8 warps each
-  uint64_t* p_full = s_free + 2;                        // [2]  8 warps each
-  uint64_t* pv_done = p_full + 2;                       // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pv_done + 2);
-  float* xch = reinterpret_cast<float*>(tmem_ptr + 4);  // [tile][half][128 rows] exchange of half-row max / sum
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int head = blockIdx.y;
-  const int q0 = blockIdx.x * 256;
-  const int qcol = head * 64, kcol = (p.heads + head) * 64, vcol = (2 * p.heads + head) * 64;
-  const int nkv = p.nkv;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm);
-    mbar_init(q_full, 1);
-    for (int i = 0; i < A4_KS; ++i) {
-      mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 2);
-    }
-    for (int i = 0; i < A4_VS; ++i) {
-      mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 2);
-    }
-    for (int t = 0; t < 2; ++t) {
-      mbar_init(&s_full[t], 1);
-      mbar_init(&s_free[t], 8);
-      mbar_init(&p_full[t], 8);
-      mbar_init(&pv_done[t], 1);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 1) tmem_alloc<512>(tmem_ptr);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-
-  if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    if (warp == 0 && elect_one()) {
-      // ===================== TMA producer =====================
-      mbar_expect_tx(q_full, 2 * ATT_TILE_BYTES);
-      tma_load_2d(sQ, &tm, q_full, qcol, q0);
-      tma_load_2d(sQ + ATT_TILE_BYTES, &tm, q_full, qcol, q0 + 128);
-      int ks = 0, vs = 0;
-      uint32_t kph = 0, vph = 0;
-      for (int j = 0; j < nkv; ++j) {
-        mbar_wait(&k_empty[ks], kph ^ 1);
-        mbar_expect_tx(&k_full[ks], ATT_TILE_BYTES);
-        tma_load_2d(sK + ks * ATT_TILE_BYTES, &tm, &k_full[ks], kcol, j * 128);
-        if (++ks == A4_KS) ks = 0, kph ^= 1;
-        mbar_wait(&v_empty[vs], vph ^ 1);
-        mbar_expect_tx(&v_full[vs], ATT_TILE_BYTES);
-        tma_load_2d(sV + vs * ATT_TILE_BYTES, &tm, &v_full[vs], vcol, j * 128);
-        if (++vs == A4_VS) vs = 0, vph ^= 1;
-      }
-    } else if ((warp == 1 || warp == 2) && elect_one()) {
-      // ===================== MMA issuers (as v4): warp 1 drives query tile 0, warp 2 query tile 1 =====================
-      const int t = warp - 1;
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // Q (K-major) x K (K-major)
-      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);    // P (TMEM) x V (MN-major)
-      const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ + t * ATT_TILE_BYTES));
-      const uint64_t kdesc0 = umma_desc_sw128(smem_u32(sK));
-      const uint64_t vdesc0 = umma_desc_sw128(smem_u32(sV));
-      const uint32_t TS = tmem_base + t * 256, TO = TS + 128, TP = TS + 192;
-      auto issue_s = [&](int kstage) {
-        const uint64_t kdesc = kdesc0 + static_cast<uint64_t>(kstage) * (ATT_TILE_BYTES >> 4);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_ss(TS, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
-        umma_commit(&s_full[t]);
-        umma_commit(&k_empty[kstage]);
-      };
-      auto issue_pv = [&](int vstage, bool first) {
-        const uint64_t vdesc = vdesc0 + static_cast<uint64_t>(vstage) * (ATT_TILE_BYTES >> 4);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_ts(TO, TP + k * 8, vdesc + 128 * k, idesc_o, !(first && k == 0));
-        umma_commit(&pv_done[t]);
-        umma_commit(&v_empty[vstage]);
-      };
-      mbar_wait(q_full, 0);
-      mbar_wait(&k_full[0], 0);
-      tc_fence_after();
-      issue_s(0);
-      for (int n = 0; n < nkv; ++n) {
-        if (n + 1 < nkv) {
-          mbar_wait(&k_full[(n + 1) & 3], ((n + 1) >> 2) & 1);
-          mbar_wait(&s_free[t], n & 1);
-          tc_fence_after();
-          issue_s((n + 1) & 3);
-        }
-        mbar_wait(&v_full[n & 3], (n >> 2) & 1);
-        mbar_wait(&p_full[t], n & 1);
-        tc_fence_after();
-        issue_pv(n & 3, n == 0);
-      }
-    }
-  } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
-    // ===================== softmax: 16 warps, one (query row, key half) per thread =====================
-    const int w = warp - 4;
-    const int t = w >> 3;                   // query tile
-    const int half = (w >> 2) & 1;          // key columns half*64 .. +63 of every tile
-    const int q = w & 3;                    // TMEM lane quarter (== warp % 4)
-    const int r = q * 32 + lane;            // query row in tile == TMEM lane
-    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    const uint32_t TS = tmem_base + t * 256 + lane_off + half * 64;
-    const uint32_t TO = tmem_base + t * 256 + lane_off + 128 + half * 32;     // this thread's 32 of the 64 O columns
-    const uint32_t TP = tmem_base + t * 256 + lane_off + 192 + half * 32;     // 64 keys = 32 packed columns
-    float* my_x = xch + (t * 2 + half) * 128 + r;
-    const float* other_x = xch + (t * 2 + (half ^ 1)) * 128 + r;
-    const int pair_bar = 1 + t * 4 + q;     // named barrier shared with the partner warp (same rows, other key half)
-    float m_used = -INFINITY, l_run = 0.f;  // m_used: integer exponent reference, identical in both halves of a row
-    const float sl2 = p.scale_log2;
-    const float inv_sl2 = 1.0f / sl2;
-    const uint64_t sl2_2 = pack_f32x2(sl2, sl2);
-    const bool ragged = (nkv * 128 != p.rows);
-
-    for (int j = 0; j < nkv; ++j) {
-      mbar_wait(&s_full[t], j & 1);
-      tc_fence_after();
-      uint32_t v[64];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld16(TS + c * 16, v + c * 16);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_free[t]);           // S_t(j+1) may overwrite the buffer
-      if (ragged && j == nkv - 1) {
-        const int kbase = j * 128 + half * 64;
-#pragma unroll
-        for (int i = 0; i < 64; ++i)
-          if (kbase + i >= p.rows) v[i] = 0xff800000u;   // -inf
-      }
-      // ---- row maximum: own half, then the partner's through shared memory ----
-      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-      for (int i = 0; i < 64; i += 8) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          m4[u] = fmaxf(m4[u], fmaxf(__uint_as_float(v[i + 2 * u]), __uint_as_float(v[i + 2 * u + 1])));
-      }
-      float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-      *my_x = mx;
-      named_bar_sync(pair_bar, 64);
-      mx = fmaxf(mx, *other_x);
-      named_bar_sync(pair_bar, 64);                     // the slot is rewritten next tile (and by the final sum exchange)
-      const float m_new = fmaxf(m_used, fminf(fmaxf(ceilf(mx * sl2), -1048576.0f), 1048576.0f));
-      const bool need = (m_new - m_used) > ATT_LAZY_THRESHOLD;     // first tile: inf > 8
-      const bool warp_need = __any_sync(0xffffffffu, need);
-      float alpha = 1.0f;
-      if (need) {
-        alpha = ex2_approx(m_used - m_new);
-        m_used = m_new;
-      }
-      bool waited_pv = (j == 0);
-      if (j > 0 && warp_need) {              // O *= alpha on this thread's 32 head-dim columns (rare after the first tiles)
-        mbar_wait(&pv_done[t], (j - 1) & 1);
-        tc_fence_after();
-        waited_pv = true;
-        uint32_t o[32];
-        tmem_ld32(TO, o);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-        tmem_st32(TO, o);
-      }
-      // ---- exponentials ----
-      const float neg_m = -m_used;
-      const uint64_t negm_2 = pack_f32x2(neg_m, neg_m);
-      const float cm = 12582912.0f - m_used;
-      const uint64_t cm_2 = pack_f32x2(cm, cm);
-      const float smin = (m_used - 125.0f) * inv_sl2;
-      const uint64_t neg1_2 = pack_f32x2(-1.0f, -1.0f);
-      uint64_t lsA = 0ull, lsB = 0ull;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int g = c * 16 + i;
-          float p0, p1;
-          if (a3_emu_pair(i, EMU8)) {
-            const float s0 = fmaxf(__uint_as_float(v[2 * g]), smin), s1 = fmaxf(__uint_as_float(v[2 * g + 1]), smin);
-            const uint64_t s2 = pack_f32x2(s0, s1);
-            const uint64_t t2 = fma_f32x2(s2, sl2_2, cm_2);        // magic + round(x), x = s*c - m <= 0.5
-            const uint64_t d2 = fma_f32x2(t2, neg1_2, cm_2);       // -m - round(x)   (exact)
-            const uint64_t r2 = fma_f32x2(s2, sl2_2, d2);          // x - round(x) in [-0.5, 0.5]
-            uint64_t q2 = fma_f32x2(pack_f32x2(0.05517132207751274f, 0.05517132207751274f), r2,
-                                    pack_f32x2(0.24261054396629333f, 0.24261054396629333f));
-            q2 = fma_f32x2(q2, r2, pack_f32x2(0.6932609677314758f, 0.6932609677314758f));
-            q2 = fma_f32x2(q2, r2, pack_f32x2(0.9999281167984009f, 0.9999281167984009f));
-            float qa, qb, ta, tb;
-            unpack_f32x2(q2, qa, qb);
-            unpack_f32x2(t2, ta, tb);
-            p0 = __uint_as_float(__float_as_uint(qa) + (__float_as_uint(ta) << 23));
-            p1 = __uint_as_float(__float_as_uint(qb) + (__float_as_uint(tb) << 23));
-          } else {
-            const uint64_t x2 = fma_f32x2(pack_f32x2(__uint_as_float(v[2 * g]), __uint_as_float(v[2 * g + 1])), sl2_2,
-                                          negm_2);
-            float x0, x1;
-            unpack_f32x2(x2, x0, x1);
-            p0 = ex2_approx(x0);
-            p1 = ex2_approx(x1);
-          }
-          if (i & 1) lsB = add_f32x2(lsB, pack_f32x2(p0, p1));
-          else lsA = add_f32x2(lsA, pack_f32x2(p0, p1));
-          pk[i] = pack_bf16x2(p0, p1);
-        }
-        if (!waited_pv) {                    // P_t is only rewritten after PV_t(j-1) has retired
-          mbar_wait(&pv_done[t], (j - 1) & 1);
-          tc_fence_after();
-          waited_pv = true;
-        }
-        tmem_st16(TP + c * 16, pk);
-      }
-      float a0, a1, b0, b1;
-      unpack_f32x2(lsA, a0, a1);
-      unpack_f32x2(lsB, b0, b1);
-      l_run = l_run * alpha + ((a0 + a1) + (b0 + b1));
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[t]);
-    }
-    // ---- row sum of both halves, normalisation of this thread's 32 head-dim columns ----
-    *my_x = l_run;
-    named_bar_sync(pair_bar, 64);
-    l_run += *other_x;
-    mbar_wait(&pv_done[t], (nkv - 1) & 1);
-    tc_fence_after();
-    const int row = q0 + t * 128 + r;
-    const float inv = 1.0f / l_run;
-    uint4* op = reinterpret_cast<uint4*>(p.out + static_cast<long long>(row) * (p.heads * 64) + head * 64 + half * 32);
-    uint32_t o[32];
-    tmem_ld32(TO, o);
-    tmem_ld_wait();
-    if (row < p.rows) {
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        uint4 wv;
-        wv.x = pack_bf16x2(__uint_as_float(o[jj * 8 + 0]) * inv, __uint_as_float(o[jj * 8 + 1]) * inv);
-        wv.y = pack_bf16x2(__uint_as_float(o[jj * 8 + 2]) * inv, __uint_as_float(o[jj * 8 + 3]) * inv);
-        wv.z = pack_bf16x2(__uint_as_float(o[jj * 8 + 4]) * inv, __uint_as_float(o[jj * 8 + 5]) * inv);
-        wv.w = pack_bf16x2(__uint_as_float(o[jj * 8 + 6]) * inv, __uint_as_float(o[jj * 8 + 7]) * inv);
-        op[jj] = wv;
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
-  }
-}
-
-// Measured dead ends on B200 (round 2, N = 19 426, 48 heads; v3 with 1/8 emulation = 5.23-5.44 ms):
+// Measured dead ends on B200 (round 2, N = 19 426, 48 heads; shipping v4 with 1/8 emulation = 5.05-5.4 ms depending on the
+// box, 5.19 ms / tensor pipe 42 % / XU 74 % under ncu):
 //   * 64-key tiles with double-buffered S and P in TMEM (so that S(j+1) is always ready): 6.9-7.0 ms — every per-tile
 //     fixed cost (mbarrier hand-offs, tcgen05.wait::st, fences) doubles and the N = 64 QK^T MMA is shared-memory bound;
-//   * holding the whole S row (128 fp32) in registers and releasing the S buffer before the exponentials (early issue
-//     of the next QK^T): 6.3-6.5 ms — 320-thread CTAs get 168 registers per thread (the SM allocates registers for 12
-//     warps; 200 registers fail to launch), the row + P chunk spill, and the TMEM-load / compute overlap is lost;
-//   * more than 1/8 of the exponentials on the FMA pipe: slower (ncu: XU 71 %, FMA pipe 30 %, issue slots 42 % busy, MUFU
-//     instructions stalled on the MIO queue — the kernel sits at the practical throughput of the special-function path).
+//   * holding the whole S row in registers at 168 registers per thread (v3 without setmaxnreg): 6.3-6.5 ms, spills;
+//   * more than 1/8 of the exponentials on the FMA pipe: slower in v3 and v4 (the softmax warps are in-order and
+//     latency-bound: every emulated pair is 11 dependent-ish instructions against 2 MUFU issue slots);
+//   * ONE MMA issuer thread for both query tiles (fixed order or polling four barriers): 5.4-10 ms, erratic — the issuer
+//     needs ~450 clk per action and becomes the critical path; `lane == 0` instead of elect.sync made it worse still;
+//   * loading the whole S row before the first exponential: 6.4 ms (both warpgroups sit in the TMEM read together);
+//   * SIXTEEN softmax warps (each query row split between two threads, half-row maxima exchanged through shared memory
+//     and a 64-thread named barrier every tile, 96/104 registers): correct (142 attention tests) but 5.84-5.94 ms, XU
+//     69 % — 36 % more instructions (row-max pass, exchange) and the MUFU.EX2 stalls move from `wait` to `mio_throttle`;
+//     four warps per sub-partition do not keep the special-function unit busier than two;
+//   * nanosleep back-off in the TMA / MMA threads' mbarrier spins (to take their SYNCS out of the MIO queue): no change;
+//   * packed ex2.approx.bf16x2 / f16x2: two MUFU ops per instruction in SASS, same 8 clk each (profiles/microbench_sm.cu).
+// The special-function unit sustains ~74 % of its 16 results/clk/SM in this instruction mix in every variant that keeps
+// the hand-offs off the critical path; at head_dim 64 that caps the tensor pipe near 42-45 %.
 // variant: -1 = auto (v4 with 1/8 emulation for long sequences, v2 below 6 000 rows where its 2x finer CTA grain wins);
 // 0 = v2 (2 CTAs/SM, one query tile each); 1 + e (e = 0..5) = v3 with e/8 of the exponentials on the FMA pipe;
 // 7 + e (e = 0..4) = v4 (S row in registers via setmaxnreg, two MMA issuer warps) with e/8 emulated.
 // In-step A/B at cfg-2 (42 layers, N = 19 426, power-capped clocks ~1.45 GHz): v3 289.6 ms, v4 266.9 ms per clip.
 static std::atomic<int> g_attn_variant{-1};
 int set_attn_variant(int v) {
-  if (v < -1 || v > 16) return set_error(DOVE_E_BAD_ARG, "attn_variant must be -1..16");
+  if (v < -1 || v > 11) return set_error(DOVE_E_BAD_ARG, "attn_variant must be -1..11");
   g_attn_variant.store(v);
   return DOVE_OK;
 }
@@ -1328,16 +1047,6 @@ static int launch_v4(const CUtensorMap& tm, const AttnParams& p, cudaStream_t st
   return DOVE_OK;
 }
 
-template <int EMU8>
-static int launch_v5(const CUtensorMap& tm, const AttnParams& p, cudaStream_t st) {
-  static std::once_flag flag;
-  if (int e = set_smem_once(attn_fwd_v5_kernel<EMU8>, A5_SMEM, flag)) return e;
-  dim3 grid((p.rows + 255) / 256, p.heads);
-  attn_fwd_v5_kernel<EMU8><<<grid, 640, A5_SMEM, st>>>(tm, p);
-  DOVE_LAUNCH_CHECK("attn_fwd_v5_kernel");
-  return DOVE_OK;
-}
-
 static int attention_launch(const void* qkv, void* out, int rows, int heads, float scale, cudaStream_t st) {
   if (int e = ensure_init()) return e;
   DOVE_CHECK_ARG(rows > 0 && heads > 0, "attention: empty problem");
@@ -1368,11 +1077,6 @@ static int attention_launch(const void* qkv, void* out, int rows, int heads, flo
     case 9: return launch_v4<2>(tm, p, st);
     case 10: return launch_v4<3>(tm, p, st);
     case 11: return launch_v4<4>(tm, p, st);
-    case 12: return launch_v5<0>(tm, p, st);
-    case 13: return launch_v5<1>(tm, p, st);
-    case 14: return launch_v5<2>(tm, p, st);
-    case 15: return launch_v5<3>(tm, p, st);
-    case 16: return launch_v5<4>(tm, p, st);
     default: break;
   }
   static std::once_flag flag;

@@ -15,7 +15,7 @@ pk = os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")
 BURST = json.load(open(pk))["bf16_tflops"] if os.path.exists(pk) else 1590.0
 NAMES = {0: "v2 (1 Q tile/CTA, 2 CTAs/SM)", 1: "v3 emu 0/8", 2: "v3 emu 1/8", 3: "v3 emu 2/8", 4: "v3 emu 3/8",
          5: "v3 emu 4/8", 6: "v3 emu 5/8", 7: "v4 emu 0/8", 8: "v4 emu 1/8", 9: "v4 emu 2/8", 10: "v4 emu 3/8",
-         11: "v4 emu 4/8", 12: "v5 emu 0/8", 13: "v5 emu 1/8", 14: "v5 emu 2/8", 15: "v5 emu 3/8", 16: "v5 emu 4/8"}
+         11: "v4 emu 4/8"}
 
 
 def timeit(fn, flush, iters=8, warm=3):
@@ -32,7 +32,7 @@ def timeit(fn, flush, iters=8, warm=3):
     return t[len(t) // 2]
 
 
-VARIANTS = [int(v) for v in sys.argv[1:]] or list(range(17))
+VARIANTS = [int(v) for v in sys.argv[1:]] or list(range(12))
 
 
 def main():

@@ -198,14 +198,13 @@ def _attn_ref(qkv, rows, heads, scale):
     return (p @ v).transpose(0, 1).reshape(rows, heads * 64)
 
 
-@pytest.mark.parametrize("variant", [-1, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16])
+@pytest.mark.parametrize("variant", [-1, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11])
 @pytest.mark.parametrize("rows,heads", [(128, 1), (300, 2), (482, 3), (1000, 2), (4000, 2), (64, 1), (65, 1)])
 def test_attention_variants(L, variant, rows, heads):
     """Every attention kernel variant (v2: one query tile per CTA; v3: two query tiles per CTA sharing K/V, with 0..5/8
     of the exponentials on the FMA-pipe polynomial; v4 = variants 7..11: S row held in registers (setmaxnreg) so that
-    S(j+1) is issued while softmax(j) runs, 0..4/8 emulated; v5 = variants 12..16: sixteen softmax warps, every query row
-    split between two threads that exchange the row maximum each tile; -1: automatic choice) against fp32 softmax
-    attention, ragged sizes included."""
+    S(j+1) is issued while softmax(j) runs, 0..4/8 emulated; -1: automatic choice) against fp32 softmax attention, ragged
+    sizes included."""
     L.set_option("attn_variant", variant)
     try:
         qkv = randn(rows, 3 * heads * 64, seed=rows + 1)
@@ -220,7 +219,7 @@ def test_attention_variants(L, variant, rows, heads):
         L.set_option("attn_variant", L.DEFAULT_ATTN_VARIANT)
 
 
-@pytest.mark.parametrize("variant", [0, 2, 3, 5, 7, 8, 10, 12, 13, 15])
+@pytest.mark.parametrize("variant", [0, 2, 3, 5, 7, 8, 10])
 def test_attention_wide_logit_range(L, variant):
     """Scores spanning tens of nats, a dominant key that appears only in the LAST key tile and one far-below-everything
     key: the steady-state softmax (no row-max pass, stale reference max) must detect the overflow through the row sum
