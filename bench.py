@@ -563,6 +563,17 @@ def main():
         if flops_clip and not units_mode:
             line["step_tflops"] = flops_clip / (ms_step / 1e3) / 1e12
             line["step_frac_of_peak"] = line["step_tflops"] / pk["tflops"]
+        if units_mode:          # work actually executed: every unit (chunk x tile) with its overlap, by the work model
+            from dove_b200.bookkeeping import enumerate_units
+            units = enumerate_units((1, 3, F, H, W), unit_kw["chunk_len"], unit_kw["overlap_t"], unit_kw["tile_size_hw"],
+                                    unit_kw["overlap_hw"])
+            uf = sum(2.0 * clip_macs(t1 - t0, h1 - h0, w1 - w0)["total"] for (t0, t1), (h0, h1, w0, w1) in units)
+            line["units"] = {"count": len(units), "executed_tflop": uf / 1e12,
+                             "unit_shape": [units[0][0][1] - units[0][0][0], units[0][1][1] - units[0][1][0],
+                                            units[0][1][3] - units[0][1][2]]}
+            line["step_tflops"] = uf / (ms_step / 1e3) / 1e12
+            line["step_frac_of_peak"] = line["step_tflops"] / (pk["tflops"] * world)
+        line["peak_mem_gb_rank0"] = torch.cuda.max_memory_allocated() / 2 ** 30
         top = sorted(((k, v) for k, v in classes.items() if v[1] > 0), key=lambda kv: -kv[1][1])[:8]
         line["top_classes"] = [{"class": " ".join(str(x) for x in k), "launches_per_step": v[0] / args.steps,
                                 "ms_per_step": v[1] / args.steps,

@@ -63,6 +63,7 @@ _SIGS = {
     "dove_cl_to_ncthw_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "dove_gaussian_sample_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_void_p]),
     "dove_post_scale_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "dove_h2d_box_async": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
     "dove_upscale_normalize_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "dove_blend_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int,
                                 c_int64, c_int64, c_int64, c_void_p]),
@@ -204,6 +205,20 @@ def attention(qkv, out, heads, scale):
     assert qkv.shape[1] == 3 * heads * 64 and tuple(out.shape) == (rows, heads * 64)
     _call("dove_attention_bf16", _p(_bf16c(qkv)), _p(_bf16c(out)), rows, heads, scale, _stream())
     return out
+
+
+def h2d_box(src_view, dst):
+    """src_view: a [planes, rows, cols] strided view (unit stride in cols) of a HOST tensor (pinned for a truly
+    asynchronous copy); dst: a dense CUDA tensor of the same shape and dtype.  One DMA, no staging buffer."""
+    planes, rows, cols = src_view.shape
+    assert not src_view.is_cuda and dst.is_cuda and dst.is_contiguous() and dst.dtype == src_view.dtype
+    assert tuple(dst.shape) == (planes, rows, cols)
+    sp, sr, sc = src_view.stride()
+    eb = src_view.element_size()
+    assert sc == 1 and sr >= cols and (planes == 1 or (sp % sr == 0 and sp // sr >= rows)), "unsupported source strides"
+    _call("dove_h2d_box_async", c_void_p(src_view.data_ptr()), sr * eb, (sp // sr) if planes > 1 else rows,
+          _p(dst), cols * eb, rows, planes, _stream())
+    return dst
 
 
 def patchify(latent, tokens):

@@ -103,3 +103,18 @@ extern "C" int dove_init(int device) {
   g_device = device;
   return DOVE_OK;
 }
+
+extern "C" int dove_h2d_box_async(const void* src, int64_t src_row_pitch, int64_t src_rows_per_plane, void* dst,
+                                  int64_t row_bytes, int64_t rows, int64_t planes, void* stream) {
+  if (int e = ensure_init()) return e;
+  DOVE_CHECK_ARG(src && dst && row_bytes > 0 && rows > 0 && planes > 0, "h2d_box: empty copy");
+  DOVE_CHECK_ARG(src_row_pitch >= row_bytes && src_rows_per_plane >= rows, "h2d_box: box larger than the source planes");
+  cudaMemcpy3DParms p{};
+  p.srcPtr = make_cudaPitchedPtr(const_cast<void*>(src), static_cast<size_t>(src_row_pitch),
+                                 static_cast<size_t>(src_row_pitch), static_cast<size_t>(src_rows_per_plane));
+  p.dstPtr = make_cudaPitchedPtr(dst, static_cast<size_t>(row_bytes), static_cast<size_t>(row_bytes),
+                                 static_cast<size_t>(rows));
+  p.extent = make_cudaExtent(static_cast<size_t>(row_bytes), static_cast<size_t>(rows), static_cast<size_t>(planes));
+  p.kind = cudaMemcpyHostToDevice;
+  return check_cuda(cudaMemcpy3DAsync(&p, static_cast<cudaStream_t>(stream)), "cudaMemcpy3DAsync(h2d_box)");
+}

@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(256) layernorm_mod_kernel(const bf16* __restri
     const bf16* sc = scale0 ? (row < split_row ? scale0 : scale1) : nullptr;
     const bf16* sh = scale0 ? (row < split_row ? shift0 : shift1) : nullptr;
     uint4* orow = reinterpret_cast<uint4*>(out + static_cast<long long>(row) * D);
+    const __nv_bfloat162 one2 = __floats2bfloat162_rn(1.0f, 1.0f);
 #pragma unroll
     for (int i = 0; i < 16; ++i)
       if (i < nv) {
@@ -82,16 +83,27 @@ __global__ void __launch_bounds__(256) layernorm_mod_kernel(const bf16* __restri
         unpack8(v[i], f);
         unpack8(*reinterpret_cast<const uint4*>(w + col), wv);
         unpack8(*reinterpret_cast<const uint4*>(b + col), bv);
+        uint32_t n[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) f[k] = bf16_round((f[k] - mean) * rstd * wv[k] + bv[k]);
+        for (int k = 0; k < 4; ++k)      // LayerNorm in fp32, ONE rounding to bf16 (F.layer_norm's output)
+          n[k] = pack_bf16x2((f[2 * k] - mean) * rstd * wv[2 * k] + bv[2 * k],
+                             (f[2 * k + 1] - mean) * rstd * wv[2 * k + 1] + bv[2 * k + 1]);
         if (sc) {
-          float scv[8], shv[8];
-          unpack8(*reinterpret_cast<const uint4*>(sc + col), scv);
-          unpack8(*reinterpret_cast<const uint4*>(sh + col), shv);
+          // norm * (1 + scale) + shift as three bf16 tensor ops (each rounds to nearest even): packed bf16x2
+          // arithmetic gives exactly those roundings (the product / sum of two bf16 is exact in fp32) at a quarter of
+          // the instructions of the unpack -> fp32 -> round sequence; _rn forms so that mul + add never contract
+          const uint4 s4 = *reinterpret_cast<const uint4*>(sc + col);
+          const uint4 h4 = *reinterpret_cast<const uint4*>(sh + col);
+          const uint32_t sw[4] = {s4.x, s4.y, s4.z, s4.w}, hw[4] = {h4.x, h4.y, h4.z, h4.w};
 #pragma unroll
-          for (int k = 0; k < 8; ++k) f[k] = bf16_round(f[k] * bf16_round(1.0f + scv[k])) + shv[k];
+          for (int k = 0; k < 4; ++k) {
+            const __nv_bfloat162 t1 = __hadd2_rn(one2, *reinterpret_cast<const __nv_bfloat162*>(&sw[k]));
+            const __nv_bfloat162 t2 = __hmul2_rn(*reinterpret_cast<const __nv_bfloat162*>(&n[k]), t1);
+            const __nv_bfloat162 t3 = __hadd2_rn(t2, *reinterpret_cast<const __nv_bfloat162*>(&hw[k]));
+            n[k] = *reinterpret_cast<const uint32_t*>(&t3);
+          }
         }
-        orow[i * 32 + lane] = pack8(f);
+        orow[i * 32 + lane] = make_uint4(n[0], n[1], n[2], n[3]);
       }
   }
 }

@@ -38,23 +38,22 @@ def _region_numel(r, C):
 
 
 _DTYPE_NAMES = {"bfloat16": torch.bfloat16, "float32": torch.float32, "float16": torch.float16, "uint8": torch.uint8}
-_staging = {}
-
-
 def _unit_to_device(unit, dev):
-    """A unit is a strided view of the clip.  When the clip lives in (pinned) host memory only THIS unit crosses
-    PCIe: it is packed into a reusable pinned staging buffer and copied asynchronously (ref :407 copies per unit too)."""
+    """A unit is a strided [1,C,t,h,w] view of the clip.  When the clip lives in host memory only THIS unit crosses
+    PCIe (ref :407 copies per unit too): one strided DMA per channel straight out of the (pinned) clip
+    (dove_h2d_box_async = cudaMemcpy3DAsync) — no staging buffer, no CPU pass over the payload, no stream sync."""
     dev = torch.device(dev)
     if unit.device.type != "cpu" or dev.type != "cuda":
         return unit.to(dev)
-    key = (tuple(unit.shape), unit.dtype)
-    buf = _staging.get(key)
-    if buf is None:
-        _staging.clear()                                   # one live staging shape at a time
-        buf = _staging[key] = torch.empty(unit.shape, dtype=unit.dtype).pin_memory()
-    torch.cuda.current_stream(dev).synchronize()           # the previous unit's async H2D has left the buffer
-    buf.copy_(unit)
-    return buf.to(dev, non_blocking=True)
+    B, C, t, h, w = unit.shape
+    st = unit.stride()
+    if B != 1 or st[4] != 1 or (t > 1 and st[2] % st[3] != 0):
+        return unit.to(dev)                                # exotic layout: let torch stage it
+    from . import _lib as L
+    out = torch.empty((1, C, t, h, w), dtype=unit.dtype, device=dev)
+    for c in range(C):
+        L.h2d_box(unit[0, c], out[0, c])
+    return out
 
 
 def super_resolve(video, process_fn, *, chunk_len=0, overlap_t=8, tile_size_hw=(0, 0), overlap_hw=(32, 32),

@@ -193,6 +193,13 @@ int dove_cl_to_ncthw_bf16(const void* x, void* y, int C, int T, int H, int W, in
 int dove_gaussian_sample_bf16(const void* moments, const void* noise, void* z, int64_t nvox, float scaling,
                               void* stream);
 
+/* Host -> device copy of a strided box without a staging pass: `planes` planes of `rows` rows of `row_bytes` bytes, read
+ * from (pinned) host memory with row pitch `src_row_pitch` bytes and `src_rows_per_plane` rows between plane starts,
+ * written densely to dst.  One cudaMemcpy3DAsync (a DMA descriptor, no CPU touch of the payload).  Replaces the
+ * per-unit `video_chunk.to(device)` of a chunk x tile view of the clip (ref: inference_script.py:407, :690-700). */
+int dove_h2d_box_async(const void* src, int64_t src_row_pitch, int64_t src_rows_per_plane, void* dst, int64_t row_bytes,
+                       int64_t rows, int64_t planes, void* stream);
+
 /* Pre-processing of the low-quality clip on the GPU (ref: inference_script.py:672-679): lr [F,3,h,w] fp32 in 0..255
  * -> out [3, F, scale*h, scale*w] fp32 = bilinear (align_corners=False) upscale, then x/255*2-1. */
 int dove_upscale_normalize_f32(const float* lr, float* out, int F, int h, int w, int scale, void* stream);

@@ -33,13 +33,14 @@ def timeit(fn, flush, iters=8, warm=3):
 
 
 VARIANTS = [int(v) for v in sys.argv[1:]] or list(range(12))
+NS = [int(v) for v in os.environ.get("DOVE_ATTN_NS", "19426,2618,32866").split(",")]   # 3216 / 4978 = cfg-3 / cfg-4 units
 
 
 def main():
     L.init(0)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     heads = 48
-    for n in (19426, 2618, 32866):
+    for n in NS:
         g = torch.Generator(device="cuda").manual_seed(n)
         qkv = torch.randn(n, 3 * heads * 64, generator=g, device="cuda").bfloat16()
         q, k, v = [t.float().reshape(n, heads, 64).transpose(0, 1) for t in qkv.chunk(3, dim=1)]

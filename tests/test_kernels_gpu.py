@@ -546,3 +546,25 @@ def test_conv_fused_groupnorm_stats(L, cin, cout, T, H, W):
         torch.cuda.synchronize()
         assert torch.isfinite(fused).all()
         assert torch.allclose(fused, ref, rtol=2e-4, atol=2e-5), (fused - ref).abs().max()
+
+
+def test_h2d_box_strided_dma(L):
+    """dove_h2d_box_async: a chunk x tile view of a pinned host clip lands on the device bit for bit (fp32 and uint8,
+    first / interior / last tile, single-frame chunk) — the per-unit H2D of runner.super_resolve."""
+    from dove_b200.runner import _unit_to_device
+    torch.manual_seed(3)
+    clip = torch.rand(1, 3, 9, 40, 56).pin_memory()
+    for (t0, t1, h0, h1, w0, w1) in [(0, 9, 0, 16, 0, 24), (2, 7, 8, 40, 16, 56), (4, 5, 24, 40, 32, 56), (0, 9, 0, 40, 0, 56)]:
+        unit = clip[:, :, t0:t1, h0:h1, w0:w1]
+        got = _unit_to_device(unit, "cuda")
+        torch.cuda.synchronize()
+        assert got.is_contiguous() and torch.equal(got.cpu(), unit.contiguous())
+    u8 = (clip * 255).to(torch.uint8).pin_memory()
+    dst = torch.empty(5, 16, 24, dtype=torch.uint8, device="cuda")
+    L.h2d_box(u8[0, 1, 2:7, 8:24, 16:40], dst)
+    torch.cuda.synchronize()
+    assert torch.equal(dst.cpu(), u8[0, 1, 2:7, 8:24, 16:40])
+    pageable = torch.rand(1, 3, 4, 32, 32)                  # pageable source: still correct (the driver stages it)
+    got = _unit_to_device(pageable[:, :, 1:3, 8:24, 0:16], "cuda")
+    torch.cuda.synchronize()
+    assert torch.equal(got.cpu(), pageable[:, :, 1:3, 8:24, 0:16])
