@@ -18,7 +18,7 @@ _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "libdove_b200.so"
 
 EPI_BIAS, EPI_GELU_TANH, EPI_GATED_RES, EPI_ADD = 0, 1, 2, 3
-DEFAULT_ATTN_VARIANT = -1     # auto: v4 kernel with 1/8 of the exps on the FMA pipe for >= 6000 rows, v2 kernel below
+DEFAULT_ATTN_VARIANT = -1     # auto: v4 kernel with 1/8 of the exps on the FMA pipe for >= 3000 rows, v2 kernel below
 
 
 class DoveError(RuntimeError):

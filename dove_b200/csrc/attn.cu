@@ -1007,7 +1007,8 @@ attn_fwd_v4_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
 //   * packed ex2.approx.bf16x2 / f16x2: two MUFU ops per instruction in SASS, same 8 clk each (profiles/microbench_sm.cu).
 // The special-function unit sustains ~74 % of its 16 results/clk/SM in this instruction mix in every variant that keeps
 // the hand-offs off the critical path; at head_dim 64 that caps the tensor pipe near 42-45 %.
-// variant: -1 = auto (v4 with 1/8 emulation for long sequences, v2 below 6 000 rows where its 2x finer CTA grain wins);
+// variant: -1 = auto (v4 with 1/8 emulation from 3 000 rows — on par with v2 at 3 216 / 4 978, ahead above —, v2 below,
+// where its 2x finer CTA grain wins);
 // 0 = v2 (2 CTAs/SM, one query tile each); 1 + e (e = 0..5) = v3 with e/8 of the exponentials on the FMA pipe;
 // 7 + e (e = 0..4) = v4 (S row in registers via setmaxnreg, two MMA issuer warps) with e/8 emulated.
 // In-step A/B at cfg-2 (42 layers, N = 19 426, power-capped clocks ~1.45 GHz): v3 289.6 ms, v4 266.9 ms per clip.
@@ -1064,7 +1065,7 @@ static int attention_launch(const void* qkv, void* out, int rows, int heads, flo
   p.scale_log2 = scale * 1.4426950408889634f;
   p.out = static_cast<bf16*>(out);
   int variant = g_attn_variant.load();
-  if (variant < 0) variant = rows >= 6000 ? 8 : 0;
+  if (variant < 0) variant = rows >= 3000 ? 8 : 0;
   switch (variant) {
     case 1: return launch_v3<0>(tm, p, st);
     case 2: return launch_v3<1>(tm, p, st);
