@@ -12,7 +12,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libdove_b200.so"
-SOURCES = ["common.cu", "gemm.cu", "gemm2.cu", "conv2.cu", "conv3.cu", "attn.cu", "elementwise.cu"]
+SOURCES = ["common.cu", "gemm.cu", "gemm2.cu", "conv2.cu", "conv3.cu", "conv4.cu", "attn.cu", "elementwise.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

@@ -17,6 +17,8 @@ namespace dove {
 
 int conv2cta_dispatch(const void* x, const void* x_prev, int Tin, const void* w, int Tout, int Hin, int Win, int Cin,
                       int Cout_pad, int kt, int Ho, int Wo, GemmParams p, cudaStream_t st);
+int conv_trans_halo_dispatch(const void* x, const void* x_prev, int Tin, const void* w, int Tout, int Hin, int Win, int Cin,
+                             int Cout_pad, int kt, int Ho, int Wo, GemmParams p, cudaStream_t st);
 int conv_narrow_dispatch(const void* x, const void* x_prev, int Tin, const void* w, int Tout, int H, int W, int Cin,
                          GemmParams p, cudaStream_t st);
 int get_option_conv2cta();
@@ -490,6 +492,37 @@ static int conv_impl(const void* x, const void* x_prev, int cached, const void* 
   // 128-channel-out convs on large images: swapped operand roles (weights = M 128, voxels = N 256)
   const bool trans = get_option_conv2cta() != 0 && stride == 1 && out_mode == 0 && Cout_pad == 128 &&
                      cout_valid == 128 && static_cast<long long>(Ho) * Wo >= 4096;
+  if (trans && get_option_conv2cta() == 1 && kh == 3 && kw == 3 && pad == 1 && Hin == Ho && Win == Wo && Wo >= 256 &&
+      (kt == 1 || kt == 3) && static_cast<long long>(Wo) * 10 >= static_cast<long long>((Wo + 255) / 256) * 256 * 9) {
+    // one image row of 256 voxels per tile + W-tap reuse out of a 258-voxel halo box (conv4.cu)
+    GemmParams q{};
+    q.Ho = Ho;
+    q.Wo = Wo;
+    q.kh = 3;
+    q.kw = 3;
+    q.stride = 1;
+    q.pad = 1;
+    q.t_shift = t_shift;
+    q.has_prev = has_prev;
+    if (gn_partial && gn_done) {
+      if (int e = check_cuda(cudaMemsetAsync(gn_partial, 0, sizeof(float) * GN_PARTIAL_ROWS * 64,
+                                             static_cast<cudaStream_t>(stream)), "gn partial memset")) return e;
+      q.gn_partial = gn_partial;
+      q.gn_cpg = 4;
+      *gn_done = 1;
+    }
+    q.epi = epilogue;
+    q.C = static_cast<bf16*>(y);
+    q.ldc = ldy;
+    q.bias = static_cast<const bf16*>(bias);
+    q.aux = static_cast<const bf16*>(aux);
+    q.ld_aux = ld_aux;
+    q.n_valid = cout_valid;
+    q.out_mode = 0;
+    q.rows_total = static_cast<long long>(Tout) * Ho * Wo;
+    return conv_trans_halo_dispatch(x, has_prev ? x_prev : nullptr, Tin_all, w, Tout, Hin, Win, Cin, Cout_pad, kt, Ho, Wo,
+                                    q, static_cast<cudaStream_t>(stream));
+  }
   if (trans) {
     int best_tw = 256;
     long long best_cost = -1;

@@ -48,7 +48,9 @@ int dove_init(int device);
 const char* dove_last_error(void);
 int dove_num_sms(void);
 /* Tuning / test switches.  "conv2cta": 1 (default) = big stride-1 3x3(x3) convs on images >= 256 wide run on the
- * CTA-pair kernel (cta_group::2 MMA + in-smem reuse of the W taps), 0 = always the 1-CTA kernel (tests).
+ * specialised kernels (256 output channels: CTA pair, cta_group::2 MMA + in-smem reuse of the W taps; 128 output
+ * channels: swapped operands + W-tap reuse out of a 258-voxel halo row), 2 = the same without the halo-row kernel
+ * (A/B runs, tests of the generic swapped-operand kernel), 0 = always the generic 1-CTA kernel (tests).
  * "attn_variant": -1 (default) = automatic; 0 = one query tile per CTA, two CTAs per SM (round-1 kernel, best below
  * ~3 000 rows); 1 + e (e = 0..5) = two query tiles per CTA sharing the K/V stages, no row-max pass in the steady state,
  * e/8 of the softmax exponentials evaluated on the FMA pipe; 7 + e (e = 0..4) = the same tiling with the S row held in

@@ -452,15 +452,20 @@ def test_layout_and_sampling(L):
     assert torch.equal(o.float(), rb(rb(rb(noise.float() * 0.5) + 0.5).clamp(0, 1)))
 
 
-@pytest.mark.parametrize("variant", [1, 0])
+@pytest.mark.parametrize("variant", [1, 2, 0])
 @pytest.mark.parametrize("cin,cout,T,H,W,kt", [(128, 128, 2, 6, 256, 3), (128, 256, 2, 5, 384, 3), (256, 256, 2, 4, 320, 1),
                                                (256, 128, 1, 8, 256, 3), (64, 128, 3, 3, 640, 3),
                                                # Cout = 128 on >= 4096-voxel frames: swapped-operand kernel (N = 256 voxels)
                                                (128, 128, 2, 16, 256, 3), (256, 128, 1, 24, 200, 3), (64, 128, 2, 64, 64, 1),
-                                               (128, 128, 3, 33, 136, 3)])
+                                               (128, 128, 3, 33, 136, 3),
+                                               # ... and, when 256-voxel row tiles fill >= 90 % of the width, its halo-row
+                                               # variant (conv4.cu): exact / ragged widths, kt = 1 and 3, 64..256 in-channels
+                                               (128, 128, 2, 9, 512, 3), (64, 128, 1, 17, 496, 3), (256, 128, 1, 16, 256, 1),
+                                               (128, 128, 1, 5, 1280, 3), (128, 128, 2, 8, 752, 1)])
 def test_conv_cta_pair(L, cin, cout, T, H, W, kt, variant):
-    """Wide stride-1 3x3(x3) convs: CTA-pair kernel (cta_group::2 + W-tap reuse through shifted smem descriptors).
-    variant 1 = CTA-pair kernel (shipping), 0 = 1-CTA kernel on the same problem."""
+    """Wide stride-1 3x3(x3) convs on the specialised kernels: CTA pair (cta_group::2 + W-tap reuse through shifted smem
+    descriptors, Cout = 256), swapped operands (Cout = 128) and its halo-row variant.  variant 1 = shipping dispatch,
+    2 = without the halo-row kernel (the generic swapped-operand kernel on the same problem), 0 = 1-CTA kernel."""
     L.set_option("conv2cta", variant)
     try:
         x = randn(T + kt - 1, H, W, cin, seed=1)
@@ -496,11 +501,11 @@ def test_preprocess_matches_reference_recipe(L):
 
 
 @pytest.mark.parametrize("cin,cout,T,H,W", [(64, 64, 3, 12, 20), (128, 128, 2, 16, 256), (128, 256, 3, 6, 384),
-                                            (256, 128, 1, 24, 200), (512, 512, 2, 12, 20)])
+                                            (256, 128, 1, 24, 200), (512, 512, 2, 12, 20), (128, 128, 3, 9, 512)])
 def test_conv3d_causal_zero_copy_cache(L, cin, cout, T, H, W):
     """dove_conv3d_causal_bf16 (two preceding frames through a second tensor map / frame-0 replication) must be
-    bit-identical to the same kernel run on the materialised padded input, for the generic, swapped-operand and
-    CTA-pair kernels."""
+    bit-identical to the same kernel run on the materialised padded input, for the generic, swapped-operand (halo-row
+    variant at 128 -> 128, 16 x 256 and 9 x 512) and CTA-pair kernels."""
     x = randn(T, H, W, cin, seed=1)
     prev = randn(2, H, W, cin, seed=2)
     K = 27 * cin
@@ -523,7 +528,7 @@ def test_conv3d_causal_zero_copy_cache(L, cin, cout, T, H, W):
 
 @pytest.mark.parametrize("cin,cout,T,H,W", [(128, 128, 2, 16, 256), (256, 128, 1, 24, 200), (128, 256, 2, 6, 384),
                                             (256, 512, 2, 5, 320), (64, 128, 2, 12, 20), (256, 256, 2, 26, 23),
-                                            (512, 512, 1, 13, 12)])
+                                            (512, 512, 1, 13, 12), (128, 128, 2, 11, 496)])
 def test_conv_fused_groupnorm_stats(L, cin, cout, T, H, W):
     """GroupNorm statistics of the conv OUTPUT accumulated in the conv epilogue (swapped-operand and CTA-pair kernels)
     equal the statistics of a separate pass over the stored tensor (generic, swapped-operand and CTA-pair kernels)."""
