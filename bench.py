@@ -22,7 +22,7 @@ the timed region (N = 1: `process_video`, bf16 result as the reference returns i
 each rank copies only its own tiles, uint8 result, D2H on rank 0).
 `families`: EVERY C-ABI call inside the timed region is bracketed by CUDA events on the launching stream; the table
 (conv / attn / gemm / norm / other / idle) sums to the step.  `roofline`: the conv launch class with the largest summed
-time (cfg-2: the 128->128 3x3x3 causal convs at full resolution on `umma_gemm_kernel<256,conv,trans>`): algorithmic
+time (cfg-2: the 128->128 3x3x3 causal convs at full resolution on `conv_trans_halo_kernel`): algorithmic
 FLOPs of one launch / its mean event duration, against MEASURED_PEAKS.json.
 """
 from __future__ import annotations
@@ -259,6 +259,8 @@ def conv_kernel_name(cin, cout, kt, Ho, Wo, stride):
     if stride == 1 and cout % 256 == 0 and Wo >= 256:
         return "conv2cta_kernel<256>"
     if stride == 1 and cout == 128 and Ho * Wo >= 4096:
+        if Wo >= 256:                                              # same rule as conv_impl (gemm.cu)
+            return "conv_trans_halo_kernel"
         return "umma_gemm_kernel<256,conv,trans>"
     bn = 256 if cout % 256 == 0 else 128 if cout % 128 == 0 else 64 if cout % 64 == 0 else 32 if cout % 32 == 0 else 16
     return f"umma_gemm_kernel<{bn},conv>"

@@ -493,7 +493,7 @@ static int conv_impl(const void* x, const void* x_prev, int cached, const void* 
   const bool trans = get_option_conv2cta() != 0 && stride == 1 && out_mode == 0 && Cout_pad == 128 &&
                      cout_valid == 128 && static_cast<long long>(Ho) * Wo >= 4096;
   if (trans && get_option_conv2cta() == 1 && kh == 3 && kw == 3 && pad == 1 && Hin == Ho && Win == Wo && Wo >= 256 &&
-      (kt == 1 || kt == 3) && static_cast<long long>(Wo) * 10 >= static_cast<long long>((Wo + 255) / 256) * 256 * 9) {
+      (kt == 1 || kt == 3)) {
     // one image row of 256 voxels per tile + W-tap reuse out of a 258-voxel halo box (conv4.cu)
     GemmParams q{};
     q.Ho = Ho;

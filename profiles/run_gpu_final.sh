@@ -12,6 +12,6 @@ echo "== gpu_library"; timeout -k 10 900 python bench.py --impl gpu_library --st
 echo "== gpu_library channels_last"; timeout -k 10 900 python bench.py --impl gpu_library --steps 2 --warmup 1 --channels-last > $O/final_gpu_library_cl.log 2>&1; tail -c 700 $O/final_gpu_library_cl.log
 echo "== attention sweep"; DOVE_ATTN_NS=19426,4978,3216,32866 timeout -k 10 600 python profiles/microbench_attn.py 0 2 8 > $O/final_microbench_attn.txt 2>&1; cat $O/final_microbench_attn.txt
 echo "== ncu launch list"; timeout -k 10 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $O/final_launches.csv python bench.py --steps 1 --warmup 1 --profile --no-cpu-baseline > $O/final_launches_bench.log 2>&1; tail -c 200 $O/final_launches_bench.log; wc -l $O/final_launches.csv
-echo "== ncu conv"; timeout -k 10 600 ncu --set full --clock-control none -k regex:"umma_gemm_kernel" -s 2 -c 1 -o $O/r02f_conv_trans -f python profiles/ncu_targets.py conv > $O/final_ncu_conv.log 2>&1; tail -1 $O/final_ncu_conv.log
+echo "== ncu conv"; timeout -k 10 600 ncu --set full --clock-control none -k regex:"conv_trans_halo_kernel" -s 2 -c 1 -o $O/r02f_conv_trans -f python profiles/ncu_targets.py conv > $O/final_ncu_conv.log 2>&1; tail -1 $O/final_ncu_conv.log
 timeout -k 10 600 ncu --set full --clock-control none -k regex:"conv2cta_kernel" -s 2 -c 1 -o $O/r02f_conv2cta -f python profiles/ncu_targets.py conv > $O/final_ncu_conv2.log 2>&1; tail -1 $O/final_ncu_conv2.log
 ls -la $O/*.ncu-rep | tail -4

@@ -458,10 +458,11 @@ def test_layout_and_sampling(L):
                                                # Cout = 128 on >= 4096-voxel frames: swapped-operand kernel (N = 256 voxels)
                                                (128, 128, 2, 16, 256, 3), (256, 128, 1, 24, 200, 3), (64, 128, 2, 64, 64, 1),
                                                (128, 128, 3, 33, 136, 3),
-                                               # ... and, when 256-voxel row tiles fill >= 90 % of the width, its halo-row
-                                               # variant (conv4.cu): exact / ragged widths, kt = 1 and 3, 64..256 in-channels
+                                               # ... and, from 256 voxels of width, its halo-row variant (conv4.cu): exact /
+                                               # ragged widths (narrow last MMA), kt = 1 and 3, 64..256 in-channels
                                                (128, 128, 2, 9, 512, 3), (64, 128, 1, 17, 496, 3), (256, 128, 1, 16, 256, 1),
-                                               (128, 128, 1, 5, 1280, 3), (128, 128, 2, 8, 752, 1)])
+                                               (128, 128, 1, 5, 1280, 3), (128, 128, 2, 8, 752, 1), (128, 128, 2, 12, 368, 3),
+                                               (128, 128, 1, 16, 264, 3), (64, 128, 2, 11, 300, 1)])
 def test_conv_cta_pair(L, cin, cout, T, H, W, kt, variant):
     """Wide stride-1 3x3(x3) convs on the specialised kernels: CTA pair (cta_group::2 + W-tap reuse through shifted smem
     descriptors, Cout = 256), swapped operands (Cout = 128) and its halo-row variant.  variant 1 = shipping dispatch,
