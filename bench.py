@@ -179,12 +179,14 @@ class CallTimer:
     def __enter__(self):
         self.orig = self.L._call
 
-        def timed(name, *args):
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        Event, orig, rec = torch.cuda.Event, self.orig, self.rec
+
+        def timed(name, *args):        # as little host work as possible inside the timed region: the work model runs later
+            s, e = Event(enable_timing=True), Event(enable_timing=True)
             s.record()
-            self.orig(name, *args)
+            orig(name, *args)
             e.record()
-            self.rec.append((name, s, e, self._work(name, args)))
+            rec.append((name, s, e, args))
         self.L._call = timed
         return self
 
@@ -218,7 +220,8 @@ class CallTimer:
     def result(self, step_ms_total, steps, pk):
         torch.cuda.synchronize()
         fam, classes = {}, {}
-        for name, s, e, (flops, key, nbytes) in self.rec:
+        for name, s, e, args in self.rec:
+            flops, key, nbytes = self._work(name, args)
             ms = s.elapsed_time(e)
             f = fam.setdefault(FAMILY.get(name, "other"), [0, 0.0, 0.0])
             f[0] += 1

@@ -127,15 +127,21 @@ def _stream():
 launch_count = 0   # number of C-ABI compute calls issued (bench.py reports kernel launches from this)
 
 
+_fn_cache = {}     # name -> bound foreign function (one attribute lookup per entry point, not per launch)
+
+
 def _call(name, *args):
     global launch_count
-    lib = load()
-    if _inited_device is None:
-        init()
-    rc = getattr(lib, name)(*args)
+    fn = _fn_cache.get(name)
+    if fn is None:
+        lib = load()
+        if _inited_device is None:
+            init()
+        fn = _fn_cache[name] = getattr(lib, name)
+    rc = fn(*args)
     launch_count += 1
     if rc != 0:
-        raise DoveError(f"{name} failed ({rc}): {lib.dove_last_error().decode()}")
+        raise DoveError(f"{name} failed ({rc}): {load().dove_last_error().decode()}")
 
 
 def _bf16c(t):

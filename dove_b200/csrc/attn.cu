@@ -636,12 +636,9 @@ __device__ int g_attn_trace_n[4];
 #define ATR_END(actor) do {} while (0)
 #endif
 constexpr int A4_KS = 4, A4_VS = 4;
-#ifndef A4_TOKEN
-#define A4_TOKEN 1
-#endif
 constexpr size_t A4_SMEM = 1024 + ATT_TILE_BYTES * (2 + A4_KS + A4_VS) + 256;
 
-template <int EMU8>
+template <int EMU8, bool TOKEN = true, int REG_MISC = 56, int REG_SOFTMAX = 224>
 __global__ void __launch_bounds__(384, 1)
 attn_fwd_v4_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -693,7 +690,7 @@ attn_fwd_v4_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REG_MISC));
     if (warp == 0 && elect_one()) {
       // ===================== TMA producer =====================
       mbar_expect_tx(q_full, 2 * ATT_TILE_BYTES);
@@ -762,7 +759,7 @@ attn_fwd_v4_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
       ATR_END(t);
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REG_SOFTMAX));
     // ===================== softmax =====================
     const int t = (warp - 4) >> 2;          // query tile of this warpgroup
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
@@ -823,7 +820,7 @@ attn_fwd_v4_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
           // scheduling token: the exponent arguments of piece c formally depend on a packed result of piece c - 2
           // (x * 0 + (-m) is not foldable in IEEE arithmetic), so ptxas cannot pull all MUFU.EX2 of the tile into one
           // burst ahead of the packing / row-sum work — two interleaved chains keep the MUFU queue fed instead
-          const float negm_c = (A4_TOKEN && c >= 2) ? fmaf(__uint_as_float(tok[c & 1]), 0.0f, neg_m) : neg_m;
+          const float negm_c = (TOKEN && c >= 2) ? fmaf(__uint_as_float(tok[c & 1]), 0.0f, neg_m) : neg_m;
           const uint64_t negm_c2 = pack_f32x2(negm_c, negm_c);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -1004,6 +1001,8 @@ attn_fwd_v4_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
 //     69 % — 36 % more instructions (row-max pass, exchange) and the MUFU.EX2 stalls move from `wait` to `mio_throttle`;
 //     four warps per sub-partition do not keep the special-function unit busier than two;
 //   * nanosleep back-off in the TMA / MMA threads' mbarrier spins (to take their SYNCS out of the MIO queue): no change;
+//   * v4 without the scheduling token: 5.40 ms (with: 5.06); v4 with a 40 / 232 register split: 5.53 ms (56 / 224: 5.06 —
+//     at 40 registers the MMA issuer threads spill and react late);
 //   * packed ex2.approx.bf16x2 / f16x2: two MUFU ops per instruction in SASS, same 8 clk each (profiles/microbench_sm.cu).
 // The special-function unit sustains ~74 % of its 16 results/clk/SM in this instruction mix in every variant that keeps
 // the hand-offs off the critical path; at head_dim 64 that caps the tensor pipe near 42-45 %.
@@ -1038,12 +1037,12 @@ static int launch_v3(const CUtensorMap& tm, const AttnParams& p, cudaStream_t st
   return DOVE_OK;
 }
 
-template <int EMU8>
+template <int EMU8, bool TOKEN = true, int REG_MISC = 56, int REG_SOFTMAX = 224>
 static int launch_v4(const CUtensorMap& tm, const AttnParams& p, cudaStream_t st) {
   static std::once_flag flag;
-  if (int e = set_smem_once(attn_fwd_v4_kernel<EMU8>, A4_SMEM, flag)) return e;
+  if (int e = set_smem_once(attn_fwd_v4_kernel<EMU8, TOKEN, REG_MISC, REG_SOFTMAX>, A4_SMEM, flag)) return e;
   dim3 grid((p.rows + 255) / 256, p.heads);
-  attn_fwd_v4_kernel<EMU8><<<grid, 384, A4_SMEM, st>>>(tm, p);
+  attn_fwd_v4_kernel<EMU8, TOKEN, REG_MISC, REG_SOFTMAX><<<grid, 384, A4_SMEM, st>>>(tm, p);
   DOVE_LAUNCH_CHECK("attn_fwd_v4_kernel");
   return DOVE_OK;
 }
