@@ -129,6 +129,7 @@ class CogVideoXPipeline:
         mom, (Tl, h, w) = self.vae.encode_cl(video if video.dtype in (torch.float32, BF) else video.to(BF))
         if noise is None:                                                               # ref :409 (global RNG)
             noise = torch.randn((1, 16, Tl, h, w), device=dev, dtype=BF, generator=generator)
+        assert tuple(noise.shape) == (1, 16, Tl, h, w), (tuple(noise.shape), (1, 16, Tl, h, w))
         pt = self.transformer.config.patch_size_t
         ncopy = Tl % pt if pt is not None else 0                                        # ref :411-418
         if pt is not None:

@@ -447,3 +447,22 @@ def test_cfg1_full_depth_42_layers():
     gate("cfg-1 one_step_sr 8x256x256 (42-layer DiT)", ours, o32, o16)
     for k in ("pred", "x0"):
         assert rel_l2(io[k], i32[k]) <= 1.5 * rel_l2(i16[k], i32[k]) + 2e-3, k
+
+
+def test_unit_graph_replay_equals_eager(env):
+    """make_process_fn(use_graph=True): the second and later units of a shape are CUDA-graph replays of the whole one-step
+    pipeline; the stitched clip must equal the eager run bit for bit (per-unit seeds, uint8 and bf16 outputs)."""
+    from dove_b200.runner import make_process_fn, super_resolve
+    m = env["models"]
+    pipe = m.b200_pipe(env["vsd"], env["dsd"], env["cfg"])
+    emb = m.prompt_embedding()
+    torch.manual_seed(1)
+    video = (torch.rand(1, 3, 9, 64, 96) * 2 - 1).cuda()
+    kw = dict(chunk_len=0, overlap_t=8, tile_size_hw=(48, 64), overlap_hw=(32, 32), noise_mode="per_unit", seed=7)
+    for output in ("uint8", "unit"):
+        eager = super_resolve(video, make_process_fn(pipe, emb, output=output), **kw)
+        fn = make_process_fn(pipe, emb, output=output, use_graph=True)
+        for _ in range(2):                       # second pass: every unit is a replay
+            got = super_resolve(video, fn, **kw)
+            torch.cuda.synchronize()
+            assert torch.equal(got, eager), output
