@@ -460,9 +460,12 @@ def main():
     out_dtype = torch.uint8 if units_mode else torch.bfloat16
     host_out = torch.empty((1, 3, F, H, W), dtype=out_dtype).pin_memory() if rank == 0 else None
     fn = make_process_fn(pipe, emb, output="uint8")
-    # e2e (the public API path) replays every unit after the first of a shape from a CUDA graph; `value` stays eager
-    # because its timed region brackets every launch with CUDA events (families / roofline), which a replay cannot host
-    fn_graph = fn if os.environ.get("DOVE_BENCH_NO_GRAPH") else make_process_fn(pipe, emb, output="uint8", use_graph=True)
+    # Unit runs (N > 1, --tiled, cfg-4) replay every unit after the first of a shape from a CUDA graph — the product path
+    # of the runner for same-shape units.  A replay cannot host per-launch CUDA events, so in unit mode `families` /
+    # `roofline` come from an instrumented EAGER pass of the same K steps right after the timed region (`families_source`);
+    # at N = 1 untiled (the headline line) every launch of the timed region itself is bracketed.
+    use_graph = units_mode and not os.environ.get("DOVE_BENCH_NO_GRAPH") and not args.profile
+    fn_graph = make_process_fn(pipe, emb, output="uint8", use_graph=True) if use_graph else fn
     unit_kw = dict(chunk_len=wl["chunk_len"], overlap_t=wl["overlap_t"], noise_mode="per_unit", **wl["tiled"])
     rank_timings = {}
 
@@ -470,6 +473,9 @@ def main():
         if not units_mode:
             torch.manual_seed(42)
             return pipe.one_step_sr(dev_clip, emb)
+        return super_resolve(dev_clip, fn_graph, timings=rank_timings, **unit_kw)
+
+    def step_resident_eager():
         return super_resolve(dev_clip, fn, timings=rank_timings, **unit_kw)
 
     def step_e2e():
@@ -509,20 +515,29 @@ def main():
         sampler.start()
     l0 = L.launch_count
     pk = peaks()
-    with CallTimer(L, pipe.vae) as ct:
+    families_source = "every launch of the timed region bracketed by CUDA events"
+    if use_graph:
         ms_total = timed(step_resident, args.steps)
-        table, classes = ct.result(ms_total, args.steps, pk)
+        rank_timings_timed = dict(rank_timings)        # per-rank times of the timed (graph) pass, not of the eager one
+        l0 = L.launch_count
+        with CallTimer(L, pipe.vae) as ct:
+            ms_inst = timed(step_resident_eager, args.steps)
+            table, classes = ct.result(ms_inst, args.steps, pk)
+        families_source = (f"separate instrumented eager pass of the same {args.steps} steps ({ms_inst / args.steps:.1f} ms "
+                           "per step); the timed region replays CUDA graphs, which cannot host per-launch events")
+    else:
+        with CallTimer(L, pipe.vae) as ct:
+            ms_total = timed(step_resident, args.steps)
+            table, classes = ct.result(ms_total, args.steps, pk)
     launches = L.launch_count - l0
     per_rank = None
-    if world > 1:             # last step's per-rank device times (CUDA events inside super_resolve)
-        t = torch.tensor([rank_timings.get("compute_ms", 0.0), rank_timings.get("collective_ms", 0.0),
-                          float(rank_timings.get("units", 0))], device=dev)
+    if world > 1:             # last timed step's per-rank device times (CUDA events inside super_resolve)
+        rt = rank_timings_timed if use_graph else rank_timings
+        t = torch.tensor([rt.get("compute_ms", 0.0), rt.get("collective_ms", 0.0), float(rt.get("units", 0))], device=dev)
         allt = [torch.zeros_like(t) for _ in range(world)]
         dist.all_gather(allt, t)
         per_rank = {"compute_ms": [round(x[0].item(), 2) for x in allt],
                     "collective_ms": [round(x[1].item(), 2) for x in allt], "units": [int(x[2].item()) for x in allt]}
-    if not args.profile and fn_graph is not fn:
-        step_e2e()                      # untimed: the first unit of a shape runs eagerly and captures the graph
     ms_e2e = timed(step_e2e, args.steps) if not args.profile else ms_total
     clocks = sampler.stop() if rank == 0 else None
 
@@ -570,7 +585,8 @@ def main():
                            + ", uint8 result, D2H on rank 0)"},
             "gpu_launches": launches,
             "families": table,
-            "roofline": roofline(pk, table, classes, ms_total, args.steps),
+            "families_source": families_source,
+            "roofline": roofline(pk, table, classes, ms_inst if use_graph else ms_total, args.steps),
         }
         if flops_clip and not units_mode:
             line["step_tflops"] = flops_clip / (ms_step / 1e3) / 1e12
