@@ -143,7 +143,10 @@ def main(argv=None):
     if args.is_vae_st:                                                                  # ref :643-645
         pipe.vae.enable_slicing()
         pipe.vae.enable_tiling()
-    fn = make_process_fn(pipe, emb, sr_noise_step=args.sr_noise_step, noise_step=args.noise_step, output="uint8")
+    # several units per clip (chunks / tiles) share a shape: replay them from one CUDA graph (runner.make_process_fn)
+    multi_unit = args.chunk_len > 0 or tuple(args.tile_size_hw) != (0, 0)
+    fn = make_process_fn(pipe, emb, sr_noise_step=args.sr_noise_step, noise_step=args.noise_step, output="uint8",
+                         use_graph=multi_unit)
     for path in files:
         name = os.path.basename(path)
         if video_prompt.get(name, "") != "":
