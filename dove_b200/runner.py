@@ -162,10 +162,10 @@ def make_process_fn(pipe, empty_prompt_embedding, sr_noise_step=399, noise_step=
 
     use_graph: units of one decomposition share a shape, and a small unit (one of 8 tiles of a 720p clip: ~4 400 launches
     of ~40 us) is bounded by the host's launch rate, so the whole one-step pipeline of a unit shape is captured ONCE into
-    a CUDA graph (after an eager warm-up run of the same shape) and replayed for every later unit: inputs (the unit's
+    a CUDA graph (on the SECOND eager run of that shape) and replayed for every later unit: inputs (the unit's
     pixels, its latent noise — drawn outside the graph from the unit's generator, exactly the eager draw) are copied
     into the graph's static buffers, the result is cloned out.  Bit-identical to the eager path (tests)."""
-    graphs = {}
+    graphs, seen = {}, {}
 
     def fn(unit, k, unit_seed):
         g = None
@@ -182,15 +182,17 @@ def make_process_fn(pipe, empty_prompt_embedding, sr_noise_step=399, noise_step=
         ent = graphs.get(key)
         if ent is None:
             out = pipe.one_step_sr(x, empty_prompt_embedding, sr_noise_step=sr_noise_step, noise=noise, output=output)
-            if fn.graph_error is None:
-                try:
+            seen[key] = seen.get(key, 0) + 1
+            if fn.graph_error is None and seen[key] >= 2:      # a shape is captured when it comes back (ragged edge
+                try:                                           # units that appear once per clip never pay a capture)
                     sx, sn = x.clone(), noise.clone()
                     torch.cuda.synchronize(pipe.device)
                     graph = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(graph):
                         so = pipe.one_step_sr(sx, empty_prompt_embedding, sr_noise_step=sr_noise_step, noise=sn,
                                               output=output)
-                    graphs.clear()                                         # one live unit shape at a time
+                    while len(graphs) >= 3:                                # each graph pins a pipeline's worth of
+                        graphs.pop(next(iter(graphs)))                     # activations: keep the 3 newest shapes
                     graphs[key] = (graph, sx, sn, so)
                 except RuntimeError as ex:     # capture refused (e.g. no memory for the private pool): stay on the
                     fn.graph_error = f"{type(ex).__name__}: {ex}"          # eager GPU path, and say so (fn.graph_error)
