@@ -188,7 +188,9 @@ def make_process_fn(pipe, empty_prompt_embedding, sr_noise_step=399, noise_step=
                     sx, sn = x.clone(), noise.clone()
                     torch.cuda.synchronize(pipe.device)
                     graph = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(graph):
+                    # thread_local: CUDA calls of OTHER threads (NCCL watchdog event queries, samplers) must not
+                    # invalidate the capture
+                    with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                         so = pipe.one_step_sr(sx, empty_prompt_embedding, sr_noise_step=sr_noise_step, noise=sn,
                                               output=output)
                     while len(graphs) >= 3:                                # each graph pins a pipeline's worth of
