@@ -467,3 +467,16 @@ def test_unit_graph_replay_equals_eager(env):
             torch.cuda.synchronize()
             assert torch.equal(got, eager), output
         assert fn.uses_graph() and fn.graph_error is None
+
+
+@pytest.mark.parametrize("F", [1, 8, 9, 17, 20])
+def test_latent_frames_matches_encoder(env, F):
+    """vae.latent_frames(F) (the noise shape the graph-replay path draws outside the captured region) is the number of
+    latent frames the encoder really produces."""
+    m = env["models"]
+    pipe = m.b200_pipe(env["vsd"], env["dsd"], env["cfg"])
+    torch.manual_seed(F)
+    video = (torch.rand(1, 3, F, 32, 32) * 2 - 1).cuda()
+    mom, (Tl, h, w) = pipe.vae.encode_cl(video)
+    torch.cuda.synchronize()
+    assert Tl == pipe.vae.latent_frames(F) and (h, w) == (4, 4)
