@@ -313,17 +313,6 @@ class AutoencoderKLCogVideoX:
         dec["limit_h"], dec["limit_w"] = smin_h - dec["blend_h"], smin_w - dec["blend_w"]
         return enc, dec
 
-    def latent_frames(self, F):
-        """Latent frames the encoder produces for F pixel frames: the frame batches of `frame_batches`, each through the
-        two compress-time stages (odd T keeps its first frame: 1 + (T-1)//2, even T halves)."""
-        n = 0
-        for (s, e) in self.frame_batches(F, self.num_sample_frames_batch_size):
-            T = e - s
-            for _ in range(2):
-                T = 1 + (T - 1) // 2 if T % 2 else T // 2
-            n += T
-        return n
-
     def _encode_untiled(self, pix):
         """pix [3,F,H,W] contiguous -> moments channels-last [T',H/8,W/8,32] (frame-batched, fresh conv cache)."""
         _, F, H, W = pix.shape
