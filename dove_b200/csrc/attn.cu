@@ -606,12 +606,15 @@ attn_fwd_v3_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
 // ncu on v3 (profiles/r02_ncu_attn_v3.txt): the softmax warps spend 24 % of their samples waiting for S(j+1), which v3
 // can only issue after softmax(j) has stored all of P(j).  v4 breaks that dependency with REGISTERS instead of TMEM
 // (TMEM is full: 2 x (S 128 + O 64 + P 64) = 512 columns):
-//   * 384 threads = 3 warpgroups; `setmaxnreg` moves registers from warpgroup 0 (TMA producer, MMA issuer, 2 idle warps:
-//     168 -> 40) to the two softmax warpgroups (168 -> 232), so a softmax thread holds its whole S row (128 fp32) in
-//     registers without spilling (v3's dead end #2 was exactly this at 168 registers);
-//   * the row is loaded in two halves (the second lands while the first is exponentiated: loading all of it up front
-//     measured 6.4 ms, both warpgroups then sit in the TMEM read together), the S buffer is released at the midpoint of
-//     the tile (s_free), and the MMA warp issues S_t(j+1) = Q_t K(j+1)^T while softmax_t(j) is still computing;
+//   * 384 threads = 3 warpgroups; `setmaxnreg` moves registers from warpgroup 0 (TMA producer, two MMA issuers, 1 idle
+//     warp: 168 -> 56) to the two softmax warpgroups (168 -> 224), so a softmax thread holds its whole S row (128 fp32) in
+//     registers without spilling (v3's dead end #2 was exactly this at 168 registers; a 40 / 232 split makes the MMA
+//     issuers spill and react late: 5.53 vs 5.06 ms);
+//   * the row arrives in eight 16-column tcgen05.ld pieces, four in flight (loading all of it up front measured 6.4 ms,
+//     both warpgroups then sit in the TMEM read together); the S buffer is released at the midpoint of the tile (s_free)
+//     and the MMA warp issues S_t(j+1) = Q_t K(j+1)^T while softmax_t(j) is still computing; P of the first half of a
+//     tile is held in registers until PV_t(j-1) has retired, and a scheduling token keeps ptxas from issuing all
+//     MUFU.EX2 of a tile in one burst (5.06 vs 5.40 ms);
 //   * TWO MMA issuer threads (warp 1: query tile 0, warp 2: query tile 1), each on a fixed S_t(n+1), PV_t(n) sequence;
 //   * K and V have separate 4-stage rings (K(j+1) is consumed a whole softmax period before V(j) is released);
 //   * the exponent reference m_used is kept INTEGER (any reference is valid, the normalisation uses the same one), which
